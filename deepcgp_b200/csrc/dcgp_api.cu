@@ -1,0 +1,437 @@
+// C ABI of libdcgp.so (see include/dcgp.h): host-side orchestration of the kernels.
+// No device allocation happens here: every buffer comes from the caller; all work is stream-ordered.
+#include <string.h>
+
+#include "dcgp_kernels.cuh"
+#include "dcgp_tc.cuh"
+
+namespace dcgp {
+const char* last_error();
+
+#define DCGP_TRY(expr)            \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != DCGP_OK) return _rc; \
+  } while (0)
+
+// Carves a caller-provided workspace into aligned sub-buffers (256 B) and tracks the high-water mark.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base((char*)p) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* r = (T*)(base ? base + off : nullptr);
+    off += n * sizeof(T);
+    return r;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- prepared layer
+// Opaque `prep` buffer consumed by dcgp_layer_apply: the minibatch-independent operands of one layer.
+struct Prep {
+  int M, Mp, R, RP, L;
+  float* zs;      // [M, L]  Z / lengthscale, fp32 (SIMT Kuf operand)
+  float* W;       // [(R+1)*Mp, Mp] fp32: block 0 = Lm^-1, block r = L_r^T G   (SIMT conditional operand)
+  float* Wmean;   // [RP, Mp]      fp32: rows r < R = (G^T q_mu)[:, r]
+  TcPrep tc;      // split-fp16 planes of the same operands (tensor-core path)
+  size_t bytes;
+};
+
+static Prep carve_prep(const dcgp_layer_desc* d, void* buf) {
+  Prep p;
+  p.M = d->M;
+  p.Mp = (int)align_up(d->M, 64);
+  p.R = d->R;
+  p.RP = 64;
+  p.L = d->f * d->f * d->C;
+  Carver c(buf);
+  p.zs = c.take<float>((size_t)p.M * p.L);
+  p.W = c.take<float>((size_t)(p.R + 1) * p.Mp * p.Mp);
+  p.Wmean = c.take<float>((size_t)p.RP * p.Mp);
+  tc_carve_prep(p.tc, p.M, p.Mp, p.R, p.L, c.base ? c.base + align_up(c.off, 1024) : nullptr);
+  c.off = align_up(c.off, 1024) + p.tc.bytes;
+  p.bytes = align_up(c.off, 256);
+  return p;
+}
+
+struct F64Work {
+  int M, Mq, R;
+  double *Kuu, *invD, *Linv, *Kinv, *Wr, *beta, *Lpinv, *invDp, *tmpMR, *sc;
+  void* trws;
+  size_t bytes;
+};
+
+static F64Work carve_f64(int M, int R, void* ws) {
+  F64Work w;
+  w.M = M;
+  w.R = R;
+  w.Mq = trtri_pad(M);
+  Carver c(ws);
+  w.Kuu = c.take<double>((size_t)M * M);
+  w.invD = c.take<double>(potrf_ws_bytes(M) / sizeof(double));
+  w.Linv = c.take<double>((size_t)w.Mq * w.Mq);
+  w.trws = c.take<double>(trtri_ws_bytes(M) / sizeof(double));
+  w.Kinv = c.take<double>((size_t)M * M);      // also holds Kuu(Z_prior) / its Cholesky factor for the KL
+  w.Wr = c.take<double>((size_t)R * M * M);    // also reused as Lp^-1 L_r for the KL trace
+  w.beta = c.take<double>((size_t)M * R);
+  w.Lpinv = c.take<double>((size_t)w.Mq * w.Mq);
+  w.invDp = c.take<double>(potrf_ws_bytes(M) / sizeof(double));
+  w.tmpMR = c.take<double>((size_t)M * R);
+  w.sc = c.take<double>(8);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+// Kuu (in w.Kuu) -> Lm (in place), Lm^-1, and the stacked conditional operand:
+//   non-white: G = Kuu^-1,  W_r = L_r^T G (= C_r^T Lm^-1, C_r = Lm^-1 L_r),  beta = G q_mu        (conditionals.py:44-58)
+//   white    : G = Lm^-1,   W_r = L_r^T G,                                   beta = G^T q_mu
+static int build_operands(const F64Work& w, int white, const double* q_mu, const double* q_sqrt, int* info,
+                          cudaStream_t st) {
+  const int M = w.M, R = w.R, Mq = w.Mq;
+  DCGP_TRY(potrf_f64(w.Kuu, M, M, w.invD, info, st));
+  DCGP_TRY(trtri_f64(w.Kuu, M, M, w.invD, w.Linv, w.trws, st));
+  const double* G = w.Linv;
+  int ldg = Mq;
+  if (!white) {
+    GemmF64 g{};
+    g.m = g.n = g.k = M;
+    g.A = w.Linv; g.lda = Mq; g.transA = 1; g.lowerA = 1;
+    g.B = w.Linv; g.ldb = Mq; g.lowerB = 1;
+    g.C = w.Kinv; g.ldc = M; g.alpha = 1.0; g.batch = 1;
+    DCGP_TRY(gemm_f64(g, st));
+    G = w.Kinv;
+    ldg = M;
+  }
+  {
+    GemmF64 g{};  // W_r = L_r^T G
+    g.m = g.n = g.k = M;
+    g.A = q_sqrt; g.lda = M; g.transA = 1; g.lowerA = 1; g.strideA = (long long)M * M;
+    g.B = G; g.ldb = ldg; g.lowerB = white ? 1 : 0; g.strideB = 0;
+    g.C = w.Wr; g.ldc = M; g.strideC = (long long)M * M;
+    g.alpha = 1.0; g.batch = R;
+    DCGP_TRY(gemm_f64(g, st));
+  }
+  {
+    GemmF64 g{};  // beta = G^T q_mu
+    g.m = M; g.n = R; g.k = M;
+    g.A = G; g.lda = ldg; g.transA = 1; g.lowerA = white ? 1 : 0;
+    g.B = q_mu; g.ldb = R;
+    g.C = w.beta; g.ldc = R; g.alpha = 1.0; g.batch = 1;
+    DCGP_TRY(gemm_f64(g, st));
+  }
+  return DCGP_OK;
+}
+
+// KL[q(u) || p(u)]: GPflow gauss_kl (layers.py:145-147) == the hand-written DS/layers.py:242-256.
+// Lp/Lpinv: Cholesky factor of the prior covariance and its inverse (ignored when white).
+static int kl_terms(const F64Work& w, int white, const double* Lp, int ldp, const double* Lpinv, int ldpi,
+                    const double* q_mu, const double* q_sqrt, double* kl, cudaStream_t st) {
+  const int M = w.M, R = w.R;
+  if (white) {
+    DCGP_TRY(sumsq_f64(q_mu, M, R, R, 0, w.sc + 0, st));
+    DCGP_TRY(sumsq_f64(q_sqrt, (long long)R * M, M, M, M, w.sc + 1, st));
+  } else {
+    GemmF64 g{};  // Lp^-1 q_mu
+    g.m = M; g.n = R; g.k = M;
+    g.A = Lpinv; g.lda = ldpi; g.lowerA = 1;
+    g.B = q_mu; g.ldb = R;
+    g.C = w.tmpMR; g.ldc = R; g.alpha = 1.0; g.batch = 1;
+    DCGP_TRY(gemm_f64(g, st));
+    DCGP_TRY(sumsq_f64(w.tmpMR, M, R, R, 0, w.sc + 0, st));
+    GemmF64 h{};  // Lp^-1 L_r
+    h.m = h.n = h.k = M;
+    h.A = Lpinv; h.lda = ldpi; h.lowerA = 1; h.strideA = 0;
+    h.B = q_sqrt; h.ldb = M; h.lowerB = 1; h.strideB = (long long)M * M;
+    h.C = w.Wr; h.ldc = M; h.strideC = (long long)M * M;
+    h.alpha = 1.0; h.batch = R;
+    DCGP_TRY(gemm_f64(h, st));
+    DCGP_TRY(sumsq_f64(w.Wr, (long long)R * M, M, M, 0, w.sc + 1, st));
+    DCGP_TRY(logdiag2_f64(Lp, ldp, M, 1, 0, w.sc + 3, st));
+  }
+  DCGP_TRY(logdiag2_f64(q_sqrt, M, M, R, (long long)M * M, w.sc + 2, st));
+  return launch_kl(w.sc, M, R, white, kl, st);
+}
+
+static int check_desc(const dcgp_layer_desc* d) {
+  if (!d) { set_error("null layer descriptor"); return DCGP_ERR_ARG; }
+  if (d->kind != DCGP_LAYER_CONV && d->kind != DCGP_LAYER_SVGP_CONV) { set_error("bad layer kind %d", d->kind); return DCGP_ERR_ARG; }
+  if (d->H < d->f || d->W < d->f || d->f < 1 || d->s < 1 || d->C < 1) { set_error("bad view geometry"); return DCGP_ERR_ARG; }
+  if (d->M < 1 || d->M > 4096 || d->R < 1 || d->R > 64) { set_error("need 1<=M<=4096 and 1<=R<=64"); return DCGP_ERR_ARG; }
+  if (!(d->variance > 0) || !(d->lengthscale > 0)) { set_error("variance / lengthscale must be positive"); return DCGP_ERR_ARG; }
+  return DCGP_OK;
+}
+
+}  // namespace dcgp
+
+using namespace dcgp;
+
+extern "C" {
+
+const char* dcgp_last_error(void) { return dcgp::last_error(); }
+int dcgp_version(void) { return 100; }
+
+int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH, int* OW, int* P, int* L) {
+  if (H < f || W < f || f < 1 || s < 1 || C < 1) { set_error("bad view geometry"); return DCGP_ERR_ARG; }
+  View v = make_view(H, W, C, f, s);
+  if (OH) *OH = v.OH;
+  if (OW) *OW = v.OW;
+  if (P) *P = v.P;
+  if (L) *L = v.L;
+  return DCGP_OK;
+}
+
+int dcgp_extract_patches(const float* X, int N, int H, int W, int C, int f, int s, int layout, float* out, void* stream) {
+  if (!X || !out || N < 0 || (layout != 0 && layout != 1)) { set_error("extract_patches: bad argument"); return DCGP_ERR_ARG; }
+  if (H < f || W < f || f < 1 || s < 1 || C < 1) { set_error("bad view geometry"); return DCGP_ERR_ARG; }
+  if (N == 0) return DCGP_OK;
+  return launch_patches(X, make_view(H, W, C, f, s), N, layout, out, (cudaStream_t)stream);
+}
+
+int dcgp_kuu(const double* Z, int M, int L, double variance, double lengthscale, double jitter, double* Kuu, void* stream) {
+  if (!Z || !Kuu || M < 1 || L < 1) { set_error("kuu: bad argument"); return DCGP_ERR_ARG; }
+  return rbf_sym_f64(Z, M, L, variance, lengthscale, jitter, Kuu, (cudaStream_t)stream);
+}
+
+size_t dcgp_kuf_workspace_bytes(int M, int L) { return align_up((size_t)M * L * sizeof(float), 256) + 256; }
+
+int dcgp_kuf(const float* X, int N, int H, int W, int C, int f, int s, const double* Z, int M, double variance,
+             double lengthscale, int layout, int ldo, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (!X || !Z || !out || N < 0 || M < 1) { set_error("kuf: bad argument"); return DCGP_ERR_ARG; }
+  if (H < f || W < f || f < 1 || s < 1 || C < 1) { set_error("bad view geometry"); return DCGP_ERR_ARG; }
+  if (layout != 0 && layout != 1) { set_error("kuf: bad layout"); return DCGP_ERR_ARG; }
+  if (layout == 1 && ldo < M) { set_error("kuf: ldo < M"); return DCGP_ERR_ARG; }
+  if (N == 0) return DCGP_OK;
+  View v = make_view(H, W, C, f, s);
+  if (!ws || ws_bytes < dcgp_kuf_workspace_bytes(M, v.L)) { set_error("kuf: workspace too small"); return DCGP_ERR_WORKSPACE; }
+  if ((long long)N * v.HWC >= (1LL << 31) || (long long)N * v.P >= (1LL << 31)) { set_error("kuf: too many rows"); return DCGP_ERR_ARG; }
+  Carver c(ws);
+  float* zs = c.take<float>((size_t)M * v.L);
+  cudaStream_t st = (cudaStream_t)stream;
+  DCGP_TRY(launch_pack_z(Z, (long long)M * v.L, 1.0 / lengthscale, zs, st));
+  return launch_kuf_simt(X, v, N, zs, M, (float)variance, (float)(1.0 / lengthscale), layout, ldo, out, st);
+}
+
+size_t dcgp_cholesky_workspace_bytes(int M) { return potrf_ws_bytes(M) + 256; }
+
+int dcgp_cholesky(double* A, int M, void* ws, size_t ws_bytes, int* info, void* stream) {
+  if (!A || !info || M < 1) { set_error("cholesky: bad argument"); return DCGP_ERR_ARG; }
+  if (!ws || ws_bytes < dcgp_cholesky_workspace_bytes(M)) { set_error("cholesky: workspace too small"); return DCGP_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(info, 0, sizeof(int), st);
+  Carver c(ws);
+  return potrf_f64(A, M, M, c.take<double>(potrf_ws_bytes(M) / sizeof(double)), info, st);
+}
+
+// ---------------------------------------------------------------------------------------------- conditional()
+struct CondWork {
+  F64Work f64;
+  float *W, *Wmean, *Kt, *acc;
+  TcCondWork tc;
+  int Mp;
+  size_t bytes;
+};
+static CondWork carve_cond(int P, int M, int N, int R, void* ws) {
+  CondWork cw;
+  cw.Mp = (int)align_up(M, 64);
+  cw.f64 = carve_f64(M, R, ws);
+  Carver c(ws);
+  c.off = cw.f64.bytes;
+  const size_t T = (size_t)P * N;
+  cw.W = c.take<float>((size_t)(R + 1) * cw.Mp * cw.Mp);
+  cw.Wmean = c.take<float>((size_t)64 * cw.Mp);
+  cw.Kt = c.take<float>(T * cw.Mp);
+  cw.acc = c.take<float>(T * (R + 1));
+  tc_carve_cond(cw.tc, M, cw.Mp, R, T, c.base ? c.base + align_up(c.off, 1024) : nullptr);
+  c.off = align_up(c.off, 1024) + cw.tc.bytes;
+  cw.bytes = align_up(c.off, 256);
+  return cw;
+}
+
+size_t dcgp_conditional_workspace_bytes(int P, int M, int N, int R) { return carve_cond(P, M, N, R, nullptr).bytes; }
+
+int dcgp_conditional(const float* Kmn, const double* Kmm, const float* Knn, const double* f, const double* q_sqrt,
+                     int white, int P, int M, int N, int R, int algo, float* fmean, float* fvar, void* ws,
+                     size_t ws_bytes, int* info, void* stream) {
+  if (!Kmn || !Kmm || !Knn || !f || !q_sqrt || !fmean || !fvar || !info) { set_error("conditional: null argument"); return DCGP_ERR_ARG; }
+  if (P < 1 || M < 1 || N < 1 || R < 1 || R > 64) { set_error("conditional: bad shape"); return DCGP_ERR_ARG; }
+  CondWork cw = carve_cond(P, M, N, R, ws);
+  if (!ws || ws_bytes < cw.bytes) { set_error("conditional: workspace too small (%zu < %zu)", ws_bytes, cw.bytes); return DCGP_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(info, 0, sizeof(int), st);
+  cudaMemcpyAsync(cw.f64.Kuu, Kmm, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToDevice, st);
+  DCGP_TRY(build_operands(cw.f64, white, f, q_sqrt, info, st));
+  const int T = P * N;
+  DCGP_TRY(launch_pmn_to_tm(Kmn, P, M, N, cw.Mp, cw.Kt, st));
+  if (algo == DCGP_ALGO_TC) {
+    DCGP_TRY(tc_pack_operands(cw.tc.prep, cw.f64.Linv, cw.f64.Mq, cw.f64.Wr, cw.f64.beta, M, cw.Mp, R, st));
+    DCGP_TRY(tc_split_rows(cw.Kt, T, cw.Mp, cw.tc, st));
+    DCGP_TRY(tc_cond(cw.tc.prep, cw.tc, T, cw.Mp, R, cw.acc, fmean, st));
+  } else {
+    DCGP_TRY(launch_pack_w(cw.f64.Linv, cw.f64.Mq, cw.f64.Wr, M, cw.Mp, R, cw.W, st));
+    DCGP_TRY(launch_pack_wmean(cw.f64.beta, M, cw.Mp, R, 64, cw.Wmean, st));
+    DCGP_TRY(launch_cond_simt(cw.Kt, T, cw.Mp, cw.Mp, cw.W, cw.Wmean, R, cw.acc, fmean, st));
+  }
+  return launch_finalize_ref_layout(cw.acc, Knn, P, N, R, fvar, st);
+}
+
+// ---------------------------------------------------------------------------------------------- layer prepare
+size_t dcgp_prepare_bytes(const dcgp_layer_desc* d) {
+  if (check_desc(d)) return 0;
+  return carve_prep(d, nullptr).bytes;
+}
+size_t dcgp_prepare_workspace_bytes(const dcgp_layer_desc* d) {
+  if (check_desc(d)) return 0;
+  return carve_f64(d->M, d->R, nullptr).bytes;
+}
+
+int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
+                       const double* q_sqrt, int algo, void* prep_buf, double* kl, void* ws, size_t ws_bytes, int* info,
+                       void* stream) {
+  DCGP_TRY(check_desc(d));
+  if (!Z || !q_mu || !q_sqrt || !prep_buf || !kl || !info) { set_error("layer_prepare: null argument"); return DCGP_ERR_ARG; }
+  F64Work w = carve_f64(d->M, d->R, ws);
+  if (!ws || ws_bytes < w.bytes) { set_error("layer_prepare: workspace too small (%zu < %zu)", ws_bytes, w.bytes); return DCGP_ERR_WORKSPACE; }
+  Prep p = carve_prep(d, prep_buf);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = d->M, R = d->R, L = p.L;
+  cudaMemsetAsync(info, 0, sizeof(int), st);
+  DCGP_TRY(rbf_sym_f64(Z, M, L, d->variance, d->lengthscale, d->jitter, w.Kuu, st));   // layers.py:18-21 / DS/layers.py:184
+  DCGP_TRY(build_operands(w, d->white, q_mu, q_sqrt, info, st));
+  if (algo == DCGP_ALGO_TC) {
+    DCGP_TRY(tc_pack_operands(p.tc, w.Linv, w.Mq, w.Wr, w.beta, M, p.Mp, R, st));
+    DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+  } else {
+    DCGP_TRY(launch_pack_w(w.Linv, w.Mq, w.Wr, M, p.Mp, R, p.W, st));
+    DCGP_TRY(launch_pack_wmean(w.beta, M, p.Mp, R, p.RP, p.Wmean, st));
+  }
+  DCGP_TRY(launch_pack_z(Z, (long long)M * L, 1.0 / d->lengthscale, p.zs, st));
+  // KL.  ConvLayer: prior covariance is Kuu at the *initial* Z with the live kernel hyper-parameters
+  // (layers.py:149-150); SVGP_Layer: the current Ku (DS/layers.py:242-256).
+  const bool own_prior = (d->kind == DCGP_LAYER_CONV) && Z_prior && Z_prior != Z && !d->white;
+  if (own_prior) {
+    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, w.Kinv, st));
+    DCGP_TRY(potrf_f64(w.Kinv, M, M, w.invDp, info, st));
+    DCGP_TRY(trtri_f64(w.Kinv, M, M, w.invDp, w.Lpinv, w.trws, st));
+    DCGP_TRY(kl_terms(w, 0, w.Kinv, M, w.Lpinv, w.Mq, q_mu, q_sqrt, kl, st));
+  } else {
+    DCGP_TRY(kl_terms(w, d->white, w.Kuu, M, w.Linv, w.Mq, q_mu, q_sqrt, kl, st));
+  }
+  return DCGP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- layer apply
+struct ApplyWork {
+  float *Kt, *acc, *mean_t, *Kzx, *kdiag;
+  TcApplyWork tc;
+  size_t bytes;
+};
+static ApplyWork carve_apply(const dcgp_layer_desc* d, int n_rows, void* ws) {
+  ApplyWork a;
+  View v = make_view(d->H, d->W, d->C, d->f, d->s);
+  const size_t Mp = align_up(d->M, 64);
+  const size_t Tk = (size_t)n_rows * v.P;                                   // rows of the patch-level kernel matrix
+  const size_t T = (d->kind == DCGP_LAYER_CONV) ? Tk : (size_t)n_rows;      // columns the conditional runs over
+  Carver c(ws);
+  a.Kt = c.take<float>(Tk * Mp);
+  a.acc = c.take<float>(T * (d->R + 1));
+  a.mean_t = c.take<float>(T * d->R);
+  a.Kzx = (d->kind == DCGP_LAYER_CONV) ? nullptr : c.take<float>((size_t)n_rows * Mp);
+  a.kdiag = (d->kind == DCGP_LAYER_CONV) ? nullptr : c.take<float>((size_t)n_rows);
+  tc_carve_apply(a.tc, d->kind, d->M, (int)Mp, d->R, v.L, Tk, T, c.base ? c.base + align_up(c.off, 1024) : nullptr);
+  c.off = align_up(c.off, 1024) + a.tc.bytes;
+  a.bytes = align_up(c.off, 256);
+  return a;
+}
+
+size_t dcgp_apply_workspace_bytes(const dcgp_layer_desc* d, int n_rows, int n_rep) {
+  (void)n_rep;
+  if (check_desc(d) || n_rows < 1) return 0;
+  return carve_apply(d, n_rows, nullptr).bytes;
+}
+
+int dcgp_layer_apply(const dcgp_layer_desc* d, const void* prep_buf, const double* patch_weights, const float* X,
+                     int n_rows, int n_rep, const float* z, int algo, float* mean, float* var, float* sample, void* ws,
+                     size_t ws_bytes, void* stream) {
+  DCGP_TRY(check_desc(d));
+  if (!prep_buf || !X || !mean || !var || n_rows < 1 || n_rep < 1 || (z && !sample)) { set_error("layer_apply: bad argument"); return DCGP_ERR_ARG; }
+  View v = make_view(d->H, d->W, d->C, d->f, d->s);
+  if ((long long)n_rows * v.HWC >= (1LL << 31) || (long long)n_rows * v.P >= (1LL << 31)) { set_error("layer_apply: too many rows"); return DCGP_ERR_ARG; }
+  ApplyWork a = carve_apply(d, n_rows, ws);
+  if (!ws || ws_bytes < a.bytes) { set_error("layer_apply: workspace too small (%zu < %zu)", ws_bytes, a.bytes); return DCGP_ERR_WORKSPACE; }
+  Prep p = carve_prep(d, const_cast<void*>(prep_buf));
+  cudaStream_t st = (cudaStream_t)stream;
+  const float variance = (float)d->variance, inv_ls = (float)(1.0 / d->lengthscale);
+  const int Tk = n_rows * v.P;
+  const bool conv = d->kind == DCGP_LAYER_CONV;
+  const int T = conv ? Tk : n_rows;
+  if (algo == DCGP_ALGO_TC) {
+    DCGP_TRY(tc_layer_apply(d, v, p.tc, a.tc, patch_weights, X, n_rows, a.Kzx, a.kdiag, a.acc, a.mean_t, st));
+  } else {
+    DCGP_TRY(launch_kuf_simt(X, v, n_rows, p.zs, p.M, variance, inv_ls, 1, p.Mp, a.Kt, st));       // layers.py:112 / kernels.py:123
+    const float* Kcols = a.Kt;
+    if (!conv) {
+      DCGP_TRY(launch_patch_mean(a.Kt, n_rows, v.P, p.Mp, p.M, patch_weights, 0, p.Mp, a.Kzx, st)); // kernels.py:127-133
+      Kcols = a.Kzx;
+    }
+    DCGP_TRY(launch_cond_simt(Kcols, T, p.Mp, p.Mp, p.W, p.Wmean, p.R, a.acc, a.mean_t, st));       // conditionals.py:31-65
+  }
+  if (!conv) DCGP_TRY(launch_kdiag(X, v, n_rows, patch_weights, variance, inv_ls * inv_ls, a.kdiag, st));  // kernels.py:106-115
+  return launch_finalize(a.acc, a.mean_t, T, p.R, variance, conv ? nullptr : a.kdiag, n_rep, z, (float)d->jitter, mean, var,
+                         sample, st);
+}
+
+// ---------------------------------------------------------------------------------------------- ConvKernel API mirror
+size_t dcgp_convkernel_kzx_workspace_bytes(const dcgp_layer_desc* d, int N) {
+  if (check_desc(d) || N < 1) return 0;
+  View v = make_view(d->H, d->W, d->C, d->f, d->s);
+  const size_t Mp = align_up(d->M, 64);
+  return align_up((size_t)N * v.P * Mp * sizeof(float), 256) + align_up((size_t)d->M * v.L * sizeof(float), 256) + 256;
+}
+
+int dcgp_convkernel_kzx(const dcgp_layer_desc* d, const double* Z, const double* patch_weights, const float* X, int N,
+                        float* out, void* ws, size_t ws_bytes, void* stream) {
+  DCGP_TRY(check_desc(d));
+  if (!Z || !X || !out || N < 1) { set_error("kzx: bad argument"); return DCGP_ERR_ARG; }
+  if (!ws || ws_bytes < dcgp_convkernel_kzx_workspace_bytes(d, N)) { set_error("kzx: workspace too small"); return DCGP_ERR_WORKSPACE; }
+  View v = make_view(d->H, d->W, d->C, d->f, d->s);
+  const int Mp = (int)align_up(d->M, 64);
+  Carver c(ws);
+  float* Kt = c.take<float>((size_t)N * v.P * Mp);
+  float* zs = c.take<float>((size_t)d->M * v.L);
+  cudaStream_t st = (cudaStream_t)stream;
+  DCGP_TRY(launch_pack_z(Z, (long long)d->M * v.L, 1.0 / d->lengthscale, zs, st));
+  DCGP_TRY(launch_kuf_simt(X, v, N, zs, d->M, (float)d->variance, (float)(1.0 / d->lengthscale), 1, Mp, Kt, st));
+  return launch_patch_mean(Kt, N, v.P, Mp, d->M, patch_weights, 1, 0, out, st);
+}
+
+int dcgp_convkernel_kdiag(const dcgp_layer_desc* d, const double* patch_weights, const float* X, int N, float* out,
+                          void* stream) {
+  DCGP_TRY(check_desc(d));
+  if (!X || !out || N < 1) { set_error("kdiag: bad argument"); return DCGP_ERR_ARG; }
+  View v = make_view(d->H, d->W, d->C, d->f, d->s);
+  const float inv_ls = (float)(1.0 / d->lengthscale);
+  return launch_kdiag(X, v, N, patch_weights, (float)d->variance, inv_ls * inv_ls, out, (cudaStream_t)stream);
+}
+
+int dcgp_reparameterize(const float* mean, const float* var, const float* z, size_t n, double jitter, float* out,
+                        void* stream) {
+  if (!mean || !var || !z || !out) { set_error("reparameterize: null argument"); return DCGP_ERR_ARG; }
+  if (n == 0) return DCGP_OK;
+  return launch_reparam(mean, var, z, n, (float)jitter, out, (cudaStream_t)stream);
+}
+
+int dcgp_multiclass_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,
+                           double* varexp, double* sum, void* stream) {
+  if (!Fmu || !Fvar || !Y || !varexp || !sum || S < 1 || N < 1) { set_error("varexp: bad argument"); return DCGP_ERR_ARG; }
+  return launch_varexp(Fmu, Fvar, Y, S, N, K, epsilon, varexp, sum, (cudaStream_t)stream);
+}
+
+int dcgp_elbo(const double* sum_varexp, int S, double num_data, double n_global, const double* kls, int n_layers,
+              double* elbo, void* stream) {
+  if (!sum_varexp || !kls || !elbo || S < 1 || n_layers < 1 || !(n_global > 0)) { set_error("elbo: bad argument"); return DCGP_ERR_ARG; }
+  return launch_elbo(sum_varexp, S, num_data / n_global, kls, n_layers, elbo, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,368 @@
+// float64 "M-only" toolbox: everything whose size depends only on the number of inducing patches M.
+//   Kuu (layers.py:18-21), Cholesky (conditionals.py:29), L^-1, and the small dense products that
+//   build the stacked conditional operand W and the KL terms.  These are latency-bound at M <= 1024
+//   (Cholesky at M=512 is 45 MFLOP); tcgen05 has no fp64 kind, so they run on the fp64 CUDA cores.
+#include <stdarg.h>
+#include <string.h>
+
+#include "dcgp_common.cuh"
+
+namespace dcgp {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return DCGP_ERR_CUDA;
+  }
+  return DCGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ GEMM
+__global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
+  __shared__ double As[16][64 + 2];
+  __shared__ double Bs[16][64 + 2];
+  const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
+  const double* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
+  double* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+
+  for (int k0 = 0; k0 < g.k; k0 += 16) {
+    // whole-tile skips for triangular operands (block-uniform)
+    if (g.lowerA) {
+      if (!g.transA && k0 > i0 + 63) break;          // A[i][k], k <= i
+      if (g.transA && k0 + 15 < i0) continue;        // A[k][i], i <= k
+    }
+    if (g.lowerB) {
+      if (!g.transB && k0 + 15 < j0) continue;       // B[k][j], j <= k
+      if (g.transB && k0 > j0 + 63) break;           // B[j][k], k <= j
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;
+      int i, kk;
+      if (!g.transA) { i = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; i = idx & 63; }
+      const int gi = i0 + i, gk = k0 + kk;
+      double v = 0.0;
+      if (gi < g.m && gk < g.k) {
+        const int r = g.transA ? gk : gi, c = g.transA ? gi : gk;
+        if (!g.lowerA || c <= r) v = A[(long long)r * g.lda + c];
+      }
+      As[kk][i] = v;
+      int j, kb;
+      if (!g.transB) { kb = idx >> 6; j = idx & 63; } else { j = idx >> 4; kb = idx & 15; }
+      const int gj = j0 + j, gkb = k0 + kb;
+      double w = 0.0;
+      if (gj < g.n && gkb < g.k) {
+        const int r = g.transB ? gj : gkb, c = g.transB ? gkb : gj;
+        if (!g.lowerB || c <= r) w = B[(long long)r * g.ldb + c];
+      }
+      Bs[kb][j] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; b[u] = Bs[kk][tx * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int gi = i0 + ty * 4 + u;
+    if (gi >= g.m) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int gj = j0 + tx * 4 + v;
+      if (gj >= g.n) continue;
+      double* p = C + (long long)gi * g.ldc + gj;
+      double r = g.alpha * acc[u][v];
+      if (g.beta != 0.0) r += g.beta * (*p);
+      *p = r;
+    }
+  }
+}
+
+int gemm_f64(const GemmF64& g, cudaStream_t st) {
+  if (g.m <= 0 || g.n <= 0 || g.batch <= 0) return DCGP_OK;
+  dim3 grid(ceil_div(g.n, 64), ceil_div(g.m, 64), g.batch);
+  gemm_f64_kernel<<<grid, 256, 0, st>>>(g);
+  return check_launch("gemm_f64");
+}
+
+// ------------------------------------------------------------------------------------------ Kuu
+// layers.py:18-21 / kernels.py:135-136: variance * exp(-0.5 * |zi - zj|^2 / l^2) + jitter * I
+__global__ void __launch_bounds__(256) rbf_sym_f64_kernel(const double* __restrict__ Z, int M, int L, double variance,
+                                                          double inv_ls, double jitter, double* __restrict__ K) {
+  __shared__ double Zi[16][17], Zj[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
+  double d = 0.0;
+  for (int l0 = 0; l0 < L; l0 += 16) {
+    const int li = blockIdx.y * 16 + ty, lj = blockIdx.x * 16 + ty;
+    Zi[ty][tx] = (li < M && l0 + tx < L) ? Z[(long long)li * L + l0 + tx] * inv_ls : 0.0;
+    Zj[ty][tx] = (lj < M && l0 + tx < L) ? Z[(long long)lj * L + l0 + tx] * inv_ls : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      const double t = Zi[ty][l] - Zj[tx][l];
+      d = fma(t, t, d);
+    }
+    __syncthreads();
+  }
+  if (i < M && j < M) K[(long long)i * M + j] = variance * exp(-0.5 * d) + (i == j ? jitter : 0.0);
+}
+
+int rbf_sym_f64(const double* Z, int M, int L, double variance, double lengthscale, double jitter, double* K,
+                cudaStream_t st) {
+  dim3 grid(ceil_div(M, 16), ceil_div(M, 16));
+  rbf_sym_f64_kernel<<<grid, 256, 0, st>>>(Z, M, L, variance, 1.0 / lengthscale, jitter, K);
+  return check_launch("rbf_sym_f64");
+}
+
+// ------------------------------------------------------------------------------------------ Cholesky
+// Diagonal block: factor an nb<=64 block held in shared memory and also form its inverse (used for the panel
+// solve and as the seed of the triangular inverse).  Padding rows/cols behave as identity.
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int lda, int j0, int nb,
+                                                         double* __restrict__ invD, int* __restrict__ info) {
+  extern __shared__ double dyn_smem[];
+  double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
+  double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, j = e % NB;
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < nb && j < nb) v = (j <= i) ? A[(long long)(j0 + i) * lda + j0 + j] : 0.0;
+    s[i][j] = v;
+    x[i][j] = 0.0;
+  }
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    if (tid == 0) {
+      const double p = s[k][k];
+      if (!(p > 0.0)) {
+        atomicCAS(info, 0, j0 + k + 1);
+        s[k][k] = nan("");
+      } else {
+        s[k][k] = sqrt(p);
+      }
+    }
+    __syncthreads();
+    const double dkk = s[k][k];
+    for (int i = k + 1 + tid; i < nb; i += 256) s[i][k] /= dkk;
+    __syncthreads();
+    const int n = nb - k - 1;
+    for (int e = tid; e < n * n; e += 256) {
+      const int i = k + 1 + e / n, j = k + 1 + e % n;
+      if (j <= i) s[i][j] -= s[i][k] * s[j][k];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    A[(long long)(j0 + i) * lda + j0 + j] = (j <= i) ? s[i][j] : 0.0;
+  }
+  // inverse by forward substitution, one column per thread
+  if (tid < NB) {
+    const int c = tid;
+    x[c][c] = 1.0 / s[c][c];
+    for (int i = c + 1; i < NB; ++i) {
+      double acc = 0.0;
+      for (int k = c; k < i; ++k) acc = fma(s[i][k], x[k][c], acc);
+      x[i][c] = -acc / s[i][i];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) invD[e] = x[e / NB][e % NB];
+}
+
+// Panel solve: A[i, j0:j0+nb] <- A[i, j0:j0+nb] * inv(Ljj)^T for rows i >= j0+nb, 64 rows per CTA.
+__global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ A, int lda, int M, int j0, int nb,
+                                                         const double* __restrict__ invD) {
+  extern __shared__ double dyn_smem[];
+  double (*P)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
+  double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
+  const int r0 = j0 + nb + blockIdx.x * NB;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, j = e % NB;
+    P[i][j] = (r0 + i < M && j < nb) ? A[(long long)(r0 + i) * lda + j0 + j] : 0.0;
+    D[i][j] = invD[e];
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, c = e % NB;
+    if (r0 + i < M && c < nb) {
+      double acc = 0.0;
+      for (int k = 0; k <= c; ++k) acc = fma(P[i][k], D[c][k], acc);  // inv(Ljj) is lower: D[c][k], k <= c
+      A[(long long)(r0 + i) * lda + j0 + c] = acc;
+    }
+  }
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ A, int lda, int M) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (i < M && j < M && j > i) A[(long long)i * lda + j] = 0.0;
+}
+
+size_t potrf_ws_bytes(int M) { return (size_t)ceil_div(M, NB) * NB * NB * sizeof(double); }
+
+constexpr int kDiagSmem = 2 * NB * (NB + 1) * sizeof(double);
+
+int potrf_f64(double* A, int lda, int M, double* invD, int* info, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    attr_set = true;
+  }
+  const int nblk = ceil_div(M, NB);
+  for (int jb = 0; jb < nblk; ++jb) {
+    const int j0 = jb * NB, nb = (M - j0 < NB) ? (M - j0) : NB;
+    if (j0 > 0) {  // left-looking update of the block column with everything already factored
+      GemmF64 g{};
+      g.m = M - j0; g.n = nb; g.k = j0;
+      g.A = A + (long long)j0 * lda; g.lda = lda; g.transA = 0;
+      g.B = A + (long long)j0 * lda; g.ldb = lda; g.transB = 1;
+      g.C = A + (long long)j0 * lda + j0; g.ldc = lda;
+      g.alpha = -1.0; g.beta = 1.0; g.batch = 1;
+      int rc = gemm_f64(g, st);
+      if (rc) return rc;
+    }
+    potrf_diag_kernel<<<1, 256, kDiagSmem, st>>>(A, lda, j0, nb, invD + (size_t)jb * NB * NB, info);
+    const int rows_below = M - j0 - nb;
+    if (rows_below > 0)
+      trsm_panel_kernel<<<ceil_div(rows_below, NB), 256, kDiagSmem, st>>>(A, lda, M, j0, nb, invD + (size_t)jb * NB * NB);
+  }
+  zero_upper_kernel<<<dim3(ceil_div(M, 256), M), 256, 0, st>>>(A, lda, M);
+  return check_launch("potrf_f64");
+}
+
+// ------------------------------------------------------------------------------------------ L^-1
+int trtri_pad(int M) {
+  int nblk = ceil_div(M, NB), p = 1;
+  while (p < nblk) p *= 2;
+  return p * NB;
+}
+size_t trtri_ws_bytes(int M) {
+  const size_t Mq = trtri_pad(M);
+  return (Mq * Mq + Mq * Mq / 4 + 64) * sizeof(double);
+}
+
+__global__ void trtri_init_kernel(const double* __restrict__ L, int lda, int M, int Mq, const double* __restrict__ invD,
+                                  double* __restrict__ Lpad, double* __restrict__ Linv) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (i >= Mq || j >= Mq) return;
+  double l = (i == j) ? 1.0 : 0.0;
+  if (i < M && j < M) l = (j <= i) ? L[(long long)i * lda + j] : 0.0;
+  Lpad[(long long)i * Mq + j] = l;
+  double v = 0.0;
+  const int bi = i / NB, bj = j / NB;
+  if (bi == bj) {
+    if (bi * NB < M) v = invD[(size_t)bi * NB * NB + (i % NB) * NB + (j % NB)];
+    else v = (i == j) ? 1.0 : 0.0;
+  }
+  Linv[(long long)i * Mq + j] = v;
+}
+
+// inv([[A,0],[C,B]]) = [[A^-1,0],[-B^-1 C A^-1, B^-1]], applied level by level (block sizes 64,128,...).
+int trtri_f64(const double* L, int lda, int M, const double* invD, double* Linv, void* ws, cudaStream_t st) {
+  const int Mq = trtri_pad(M);
+  double* Lpad = (double*)ws;
+  double* T = Lpad + (size_t)Mq * Mq;
+  trtri_init_kernel<<<dim3(ceil_div(Mq, 256), Mq), 256, 0, st>>>(L, lda, M, Mq, invD, Lpad, Linv);
+  for (int sz = NB; sz < Mq; sz *= 2) {
+    const int npairs = Mq / (2 * sz);
+    const long long dstride = 2LL * sz * (Mq + 1);
+    GemmF64 g1{};  // T_p = C_p * A_p^-1
+    g1.m = g1.n = g1.k = sz;
+    g1.A = Lpad + (long long)sz * Mq; g1.lda = Mq; g1.strideA = dstride;
+    g1.B = Linv; g1.ldb = Mq; g1.lowerB = 1; g1.strideB = dstride;
+    g1.C = T; g1.ldc = sz; g1.strideC = (long long)sz * sz;
+    g1.alpha = 1.0; g1.beta = 0.0; g1.batch = npairs;
+    int rc = gemm_f64(g1, st);
+    if (rc) return rc;
+    GemmF64 g2{};  // Linv[b,a] = -B_p^-1 * T_p
+    g2.m = g2.n = g2.k = sz;
+    g2.A = Linv + (long long)sz * Mq + sz; g2.lda = Mq; g2.lowerA = 1; g2.strideA = dstride;
+    g2.B = T; g2.ldb = sz; g2.strideB = (long long)sz * sz;
+    g2.C = Linv + (long long)sz * Mq; g2.ldc = Mq; g2.strideC = dstride;
+    g2.alpha = -1.0; g2.beta = 0.0; g2.batch = npairs;
+    rc = gemm_f64(g2, st);
+    if (rc) return rc;
+  }
+  return check_launch("trtri_f64");
+}
+
+// ------------------------------------------------------------------------------------------ reductions
+__device__ __forceinline__ double block_sum_1024(double v) {
+  __shared__ double sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  v = (threadIdx.x < 32) ? sh[threadIdx.x] : 0.0;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(1024) sumsq_f64_kernel(const double* __restrict__ x, long long rows, int cols, int ld,
+                                                         int lower_period, double* __restrict__ out) {
+  double acc = 0.0;
+  const long long n = rows * cols;
+  for (long long e = threadIdx.x; e < n; e += 1024) {
+    const long long r = e / cols;
+    const int c = (int)(e % cols);
+    if (lower_period > 0 && c > (int)(r % lower_period)) continue;
+    const double v = x[r * ld + c];
+    acc = fma(v, v, acc);
+  }
+  acc = block_sum_1024(acc);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+int sumsq_f64(const double* x, long long rows, int cols, int ld, int lower_period, double* out, cudaStream_t st) {
+  sumsq_f64_kernel<<<1, 1024, 0, st>>>(x, rows, cols, ld, lower_period, out);
+  return check_launch("sumsq_f64");
+}
+
+__global__ void __launch_bounds__(1024) logdiag2_f64_kernel(const double* __restrict__ A, int lda, int M, int batch,
+                                                            long long stride, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < batch * M; e += 1024) {
+    const int b = e / M, i = e % M;
+    const double d = A[b * stride + (long long)i * lda + i];
+    acc += log(d * d);
+  }
+  acc = block_sum_1024(acc);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+int logdiag2_f64(const double* A, int lda, int M, int batch, long long stride, double* out, cudaStream_t st) {
+  logdiag2_f64_kernel<<<1, 1024, 0, st>>>(A, lda, M, batch, stride, out);
+  return check_launch("logdiag2_f64");
+}
+
+}  // namespace dcgp

@@ -1,0 +1,45 @@
+// Tensor-core (tcgen05 / TMEM / TMA) path: split-fp16 operands and the kernels that consume them (dcgp_tc.cu).
+#pragma once
+#include "dcgp_kernels.cuh"
+
+namespace dcgp {
+
+// Split-fp16 planes of one layer's minibatch-independent operands.
+//   x ~= (hi + lo) / 2^e  with hi = fp16(x * 2^e), lo = fp16(x * 2^e - hi): ~22 mantissa bits per operand, so that
+//   A*B ~= hi*hi + hi*lo + lo*hi on the fp16 tensor pipe with fp32 accumulation reproduces an fp32 GEMM.
+struct TcPrep {
+  int M, Mp, R, L, Lp;
+  void *Wh, *Wl;     // [(R+1)*Mp, Mp] fp16
+  void *Wmh, *Wml;   // [64, Mp] fp16 (mean rows, zero padded)
+  void *Zh, *Zl;     // [Mp, Lp] fp16 (Z / lengthscale)
+  float* zz;         // [Mp] |z/ls|^2 (fp32, from fp64)
+  float* scal;       // [8] device scalars: 0: W scale, 1: 1/Wscale, 2: Wmean scale, 3: 1/Wmean scale
+  size_t bytes;
+};
+void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf);
+int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double* Wr, const double* beta, int M, int Mp,
+                     int R, cudaStream_t st);
+int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st);
+
+struct TcCondWork {
+  TcPrep prep;
+  void *Kh, *Kl;  // [Tpad, Mp] fp16 planes of the kernel-matrix rows
+  size_t Tpad;
+  size_t bytes;
+};
+void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf);
+int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStream_t st);
+int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st);
+
+struct TcApplyWork {
+  TcCondWork kk;   // planes for the patch-level kernel matrix (Tk rows)
+  TcCondWork kz;   // planes for the image-level Kzx (SVGP_CONV only)
+  float* Kt32;     // [Tk, Mp] fp32 staging (SVGP_CONV patch-mean input)
+  size_t bytes;
+};
+void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, void* buf);
+int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a,
+                   const double* patch_weights, const float* X, int n_rows, float* Kzx, float* kdiag, float* acc,
+                   float* mean_t, cudaStream_t st);
+
+}  // namespace dcgp

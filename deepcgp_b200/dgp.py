@@ -1,0 +1,101 @@
+"""DGP_Base -- host-side mirror of submodules/Doubly-Stochastic-DGP/doubly_stochastic_dgp/dgp.py:35-126:
+propagate (:61-76), E_log_p_Y (:83-90), _build_likelihood (:92-98).  TensorFlow's graph/session is
+replaced by eager calls into libdcgp.so; the loop structure is the reference's.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .layers import TiledInput
+from .likelihoods import BroadcastingLikelihood
+
+
+class Minibatch(object):
+    """gpflow.params.Minibatch(X, batch, seed=0) stand-in: seeded shuffle, repeat, batch (host side)."""
+
+    def __init__(self, X, batch_size, seed=0):
+        self.X, self.batch_size = X, int(batch_size)
+        self._rng = np.random.RandomState(seed)
+        self._perm, self._pos = self._rng.permutation(len(X)), 0
+
+    def next_indices(self):
+        if self._pos + self.batch_size > len(self._perm):
+            self._perm, self._pos = self._rng.permutation(len(self.X)), 0
+        idx = self._perm[self._pos:self._pos + self.batch_size]
+        self._pos += self.batch_size
+        return idx
+
+
+class DGP_Base(object):
+    def __init__(self, X, Y, likelihood, layers, minibatch_size=None, num_samples=1, num_data=None, device="cuda",
+                 **kwargs):
+        self.num_samples = int(num_samples)
+        self.num_data = num_data or X.shape[0]                              # DS/dgp.py:49
+        self.device = torch.device(device)
+        self.X_all, self.Y_all = X, Y
+        self.minibatch_size = minibatch_size
+        self._mb = Minibatch(X, minibatch_size, seed=0) if minibatch_size else None   # DS/dgp.py:50-52
+        self.likelihood = BroadcastingLikelihood(likelihood)
+        self.layers = list(layers)
+        self._kls = torch.zeros(len(self.layers), dtype=torch.float64, device=self.device)
+        self._sum = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._elbo = torch.zeros(1, dtype=torch.float64, device=self.device)
+
+    # ------------------------------------------------------------------ DS/dgp.py:61-76
+    def propagate(self, X, full_cov=False, S=1, zs=None):
+        X = _lib.f32(X, self.device)
+        F = TiledInput(X, S)                                                # sX = tile(X[None], [S,1,1]) (:63)
+        Fs, Fmeans, Fvars = [], [], []
+        zs = zs or [None, ] * len(self.layers)
+        for layer, z in zip(self.layers, zs):
+            F, Fmean, Fvar = layer.sample_from_conditional(F, z=z, full_cov=full_cov)
+            Fs.append(F), Fmeans.append(Fmean), Fvars.append(Fvar)
+        return Fs, Fmeans, Fvars
+
+    def _build_predict(self, X, full_cov=False, S=1, zs=None):
+        Fs, Fmeans, Fvars = self.propagate(X, full_cov=full_cov, S=S, zs=zs)
+        return Fmeans[-1], Fvars[-1]
+
+    def E_log_p_Y(self, X, Y, zs=None):
+        """DS/dgp.py:83-90 -> [N, 1]"""
+        Fmean, Fvar = self._build_predict(X, full_cov=False, S=self.num_samples, zs=zs)
+        var_exp = self.likelihood.variational_expectations(Fmean, Fvar, Y)
+        return var_exp.mean(dim=0)
+
+    def _next_batch(self):
+        if self._mb is None:
+            return self.X_all, self.Y_all
+        idx = self._mb.next_indices()
+        return self.X_all[idx], self.Y_all[idx]
+
+    def _build_likelihood(self, X=None, Y=None, zs=None, n_global=None):
+        """DS/dgp.py:92-98: ELBO = sum_n E_q[log p(y_n|f_n)] * num_data/batch - sum_l KL_l, as a device scalar.
+        The whole step stays on the stream; nothing is read back here."""
+        if X is None:
+            X, Y = self._next_batch()
+        X = _lib.f32(X, self.device)
+        N = X.shape[0]
+        S = self.num_samples
+        for i, layer in enumerate(self.layers):          # minibatch-independent work once per step
+            layer.prepare()
+            layer._hold = True
+        try:
+            Fmean, Fvar = self._build_predict(X, full_cov=False, S=S, zs=zs)
+            K = Fmean.shape[2]
+            lik = self.likelihood.likelihood
+            lik.variational_expectations(Fmean.reshape(S * N, K), Fvar.reshape(S * N, K), Y, S=S, out_sum=self._sum)
+            for i, layer in enumerate(self.layers):
+                self._kls[i:i + 1].copy_(layer._kl)
+        finally:
+            for layer in self.layers:
+                layer._hold = False
+        _lib.check(_lib.lib.dcgp_elbo(_lib.ptr(self._sum), S, float(self.num_data), float(n_global or N),
+                                      _lib.ptr(self._kls), len(self.layers), _lib.ptr(self._elbo), _lib.stream()))
+        return self._elbo[0]
+
+    def compute_log_likelihood(self, X=None, Y=None, zs=None):
+        """GPflow Model.compute_log_likelihood: the ELBO as a Python float (synchronises; raises on a failed Cholesky)."""
+        elbo = self._build_likelihood(X, Y, zs)
+        for layer in self.layers:
+            _lib.raise_if_not_pd(layer._info)
+        return float(elbo.item())

@@ -1,0 +1,148 @@
+/*
+ * dcgp.h -- C ABI of libdcgp.so, the B200 (sm_100a) implementation of the conv-GP layer's
+ * doubly-stochastic variational forward pass of kekeblom/DeepCGP.
+ *
+ * The reference has no native code and no FFI: its "operator interface" for this path
+ * is the set of Python methods listed below.  Each entry point names the reference symbol
+ * (file:line under the reference checkout; DS/ = submodules/Doubly-Stochastic-DGP/doubly_stochastic_dgp/)
+ * whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *     (inputs, outputs, workspaces); the library never allocates or frees device memory;
+ *   - all calls are asynchronous and ordered on `stream` (a cudaStream_t passed as void*);
+ *   - activations are float32, row-major, contiguous; parameters (Z, q_mu, q_sqrt, patch weights,
+ *     kernel hyper-parameters) are float64 like the reference (gpflowrc:7); "M-only" linear algebra
+ *     (Kuu, Cholesky, triangular inverses, KL) is float64, "T-sized" work (T = patches x images) is
+ *     float32 / split-fp16 on the tensor cores with float32 accumulation;
+ *   - images are NHWC flattened to [rows, H*W*C]; a patch vector is ordered (dy, dx, c), c fastest, and
+ *     patch p = oy*OW + ox (views.py:32-44 + tf.extract_image_patches);
+ *   - return value: DCGP_OK, or an error code below; text via dcgp_last_error().
+ *     A non-positive-definite Kuu is reported LAPACK-style through the device int `*info`
+ *     (0 = ok, k>0 = leading minor k not PD), mirroring tf.errors.InvalidArgumentError at
+ *     conditionals.py:29 (caught at experiment.py:45-49); the call itself still returns DCGP_OK
+ *     because the pivot is only known on the device -- the Python host checks `info`.
+ */
+#ifndef DCGP_H_
+#define DCGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCGP_OK 0
+#define DCGP_ERR_ARG 1        /* bad argument / unsupported shape */
+#define DCGP_ERR_WORKSPACE 2  /* workspace too small */
+#define DCGP_ERR_NOT_PD 3     /* reserved for host-checked info */
+#define DCGP_ERR_CUDA 4       /* CUDA runtime error, see dcgp_last_error() */
+
+#define DCGP_LAYER_CONV 0      /* conv_gp/layers.py:ConvLayer (MultiOutputConvKernel)            */
+#define DCGP_LAYER_SVGP_CONV 1 /* DS/layers.py:SVGP_Layer with conv_gp/kernels.py:ConvKernel     */
+
+#define DCGP_ALGO_SIMT 0   /* fp32 CUDA-core path (validation path)                               */
+#define DCGP_ALGO_TC 1     /* tcgen05 split-fp16 tensor-core path (product path)                  */
+
+/* Geometry + hyper-parameters of one layer (constrained values, as GPflow hands them to the graph). */
+typedef struct {
+  int32_t kind;        /* DCGP_LAYER_*                                                            */
+  int32_t H, W, C;     /* input image (views.py:20-30)                                            */
+  int32_t f, s;        /* filter size, stride (dilation 1, VALID)                                 */
+  int32_t M;           /* inducing patches                                                        */
+  int32_t R;           /* gp_count (ConvLayer) / num_outputs (SVGP_Layer)                         */
+  int32_t white;       /* arguments.py:33                                                         */
+  double variance;     /* RBF variance  (models.py:115-117)                                       */
+  double lengthscale;  /* RBF lengthscale                                                         */
+  double jitter;       /* settings.jitter = 1e-3 (gpflowrc:11)                                    */
+} dcgp_layer_desc;
+
+const char* dcgp_last_error(void);
+int dcgp_version(void);
+
+/* views.py:56-68 FullView._patch_count/_patch_length/_out_image_size */
+int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH_host, int* OW_host, int* P_host, int* L_host);
+
+/* views.py:40-54 FullView.extract_patches_PNL (layout 0: [P,N,L]) / extract_patches (layout 1: [N,P,L]).
+ * Only the API mirror and tests use it; the layer path never materialises patches. */
+int dcgp_extract_patches(const float* X, int N, int H, int W, int C, int f, int s, int layout, float* out,
+                         void* stream);
+
+/* layers.py:18-21 MultiOutputConvKernel.Kuu; kernels.py:135-136,172-174 ConvKernel.Kzz + Kuu dispatch.
+ * Kuu[M,M] = variance*exp(-0.5*|zi-zj|^2/l^2) + jitter*I, float64. */
+int dcgp_kuu(const double* Z, int M, int L, double variance, double lengthscale, double jitter, double* Kuu,
+             void* stream);
+
+/* layers.py:23-32 MultiOutputConvKernel.Kuf: fused im2col + squared distance + RBF.
+ * layout 0: out[P,M,N] float32 (the reference's layout); layout 1: out[N*P, ldo] with row t = n*P+p
+ * (the layout the conditional GEMM consumes; ldo >= M, columns >= M are zero-filled).
+ * ws: dcgp_kuf_workspace_bytes(M, L) (holds Z/lengthscale in float32). */
+size_t dcgp_kuf_workspace_bytes(int M, int L);
+int dcgp_kuf(const float* X, int N, int H, int W, int C, int f, int s, const double* Z, int M,
+             double variance, double lengthscale, int layout, int ldo, float* out, void* ws, size_t ws_bytes,
+             void* stream);
+
+/* conditionals.py:29 tf.cholesky(Kmm): in-place lower Cholesky, float64, blocked left-looking.
+ * ws: dcgp_cholesky_workspace_bytes(M). *info (device int) = 0 or failing minor. */
+size_t dcgp_cholesky_workspace_bytes(int M);
+int dcgp_cholesky(double* A, int M, void* ws, size_t ws_bytes, int* info, void* stream);
+
+/* conditionals.py:6-67 conditional(Kmn, Kmm, Knn, f, full_cov=False, q_sqrt, white).
+ * Kmn[P,M,N] f32, Kmm[M,M] f64, Knn[P,N] f32, f[M,R] f64, q_sqrt[R,M,M] f64 (lower triangle used).
+ * Outputs fmean[N,P,R], fvar[R,P,N] float32 -- the reference's return layouts. */
+size_t dcgp_conditional_workspace_bytes(int P, int M, int N, int R);
+int dcgp_conditional(const float* Kmn, const double* Kmm, const float* Knn, const double* f,
+                     const double* q_sqrt, int white, int P, int M, int N, int R, int algo,
+                     float* fmean, float* fvar, void* ws, size_t ws_bytes, int* info, void* stream);
+
+/* Per-step "M-only" work of one layer (everything that does not depend on the minibatch):
+ * Kuu, Cholesky, triangular inverse, the stacked conditional operand W and the KL term.
+ *   ConvLayer : layers.py:111 (Kuu), conditionals.py:29 (Cholesky), layers.py:137-152 (KL vs Kuu(Z_prior))
+ *   SVGP_Layer: DS/layers.py:181-188 (build_cholesky_if_needed), :231-256 (KL)
+ * Z[M,L], Z_prior[M,L] or NULL (= Z), q_mu[M,R], q_sqrt[R,M,M], float64.
+ * `prep` is an opaque device buffer of dcgp_prepare_bytes() that dcgp_layer_apply consumes;
+ * kl (device double) receives the layer's KL. */
+size_t dcgp_prepare_bytes(const dcgp_layer_desc* d);
+size_t dcgp_prepare_workspace_bytes(const dcgp_layer_desc* d);
+int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
+                       const double* q_sqrt, int algo, void* prep, double* kl, void* ws, size_t ws_bytes,
+                       int* info, void* stream);
+
+/* The minibatch-sized work of one layer: layers.py:96-135 ConvLayer.conditional_ND or
+ * DS/layers.py:191-229 SVGP_Layer.conditional_ND (with kernels.py:106-133 Kzx/Kdiag), followed by the
+ * reparameterised sample of DS/layers.py:90-105 + DS/utils.py:41 when z is given.
+ *   X[n_rows, H*W*C]; logical input is `n_rep` stacked copies of X (DS/dgp.py:63 tiles the first
+ *   layer's input S times), so outputs have n_rows*n_rep rows, row = rep*n_rows + n.
+ *   z, sample: [n_rows*n_rep, D] or NULL; mean, var: [n_rows*n_rep, D];  D = P*R (conv) or R (svgp).
+ *   patch_weights[P] float64 (SVGP_CONV only; NULL = ones, kernels.py:26-28). */
+size_t dcgp_apply_workspace_bytes(const dcgp_layer_desc* d, int n_rows, int n_rep);
+int dcgp_layer_apply(const dcgp_layer_desc* d, const void* prep, const double* patch_weights, const float* X,
+                     int n_rows, int n_rep, const float* z, int algo, float* mean, float* var, float* sample,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* kernels.py:117-133 ConvKernel.Kzx -> out[M,N] f32; kernels.py:106-115 ConvKernel.Kdiag -> out[N] f32. */
+size_t dcgp_convkernel_kzx_workspace_bytes(const dcgp_layer_desc* d, int N);
+int dcgp_convkernel_kzx(const dcgp_layer_desc* d, const double* Z, const double* patch_weights, const float* X,
+                        int N, float* out, void* ws, size_t ws_bytes, void* stream);
+int dcgp_convkernel_kdiag(const dcgp_layer_desc* d, const double* patch_weights, const float* X, int N,
+                          float* out, void* stream);
+
+/* DS/utils.py:40-41 reparameterize (diag): out = mean + z*sqrt(var + jitter). */
+int dcgp_reparameterize(const float* mean, const float* var, const float* z, size_t n, double jitter,
+                        float* out, void* stream);
+
+/* DS/utils.py:88-93 -> GPflow MultiClass(RobustMax(eps=1e-3)).variational_expectations, 20-point
+ * Gauss-Hermite; Fmu,Fvar[S*N,K] f32, Y[N] int32 -> varexp[S*N] f64 and *sum (device double) = sum of
+ * varexp (DS/dgp.py:90,94 take mean over S then sum over N: divide by S on the host side). */
+int dcgp_multiclass_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K,
+                           double epsilon, double* varexp, double* sum, void* stream);
+
+/* DS/dgp.py:92-98 _build_likelihood: elbo = sum_varexp/S * (num_data/N_global) - sum_l KL_l   (device doubles) */
+int dcgp_elbo(const double* sum_varexp, int S, double num_data, double n_global, const double* kls,
+              int n_layers, double* elbo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCGP_H_ */
