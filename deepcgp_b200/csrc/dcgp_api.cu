@@ -367,7 +367,7 @@ int dcgp_layer_apply(const dcgp_layer_desc* d, const void* prep_buf, const doubl
   const bool conv = d->kind == DCGP_LAYER_CONV;
   const int T = conv ? Tk : n_rows;
   if (algo == DCGP_ALGO_TC) {
-    DCGP_TRY(tc_layer_apply(d, v, p.tc, a.tc, patch_weights, X, n_rows, a.Kzx, a.kdiag, a.acc, a.mean_t, st));
+    DCGP_TRY(tc_layer_apply(d, v, p.tc, a.tc, p.zs, a.Kt, patch_weights, X, n_rows, a.Kzx, a.acc, a.mean_t, st));
   } else {
     DCGP_TRY(launch_kuf_simt(X, v, n_rows, p.zs, p.M, variance, inv_ls, 1, p.Mp, a.Kt, st));       // layers.py:112 / kernels.py:123
     const float* Kcols = a.Kt;

@@ -2,6 +2,7 @@
 // The fp32 Kuf / conditional-GEMM kernels here are the validation path (DCGP_ALGO_SIMT); the product path
 // replaces them with the tcgen05 kernels of dcgp_tc.cu.  Glue kernels (patch gather, patch-mean, Kdiag,
 // finalize/reparameterise, RobustMax expectations, packing) are shared by both paths.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "dcgp_kernels.cuh"
@@ -32,10 +33,15 @@ int launch_patches(const float* X, const View& v, int N, int layout, float* out,
 // Fused im2col + squared distance + RBF (layers.py:23-32 with GPflow RBF.K).  64 patches x 64 inducing
 // points per CTA; the patch tile is gathered straight from the NHWC image (never materialised).
 // d = sum_l (x_l/ls - z_l/ls)^2 is formed as differences (no |x|^2+|z|^2-2xz cancellation in fp32).
+// LAYOUT 2 writes the split-fp16 planes (hi, lo of k * kscal[0]) the tensor-core conditional GEMM consumes, rows
+// t in [T, Tpad) zero-filled.
 template <int LAYOUT>
 __global__ void __launch_bounds__(256) kuf_simt_kernel(const float* __restrict__ X, View v, int T, int N,
                                                        const float* __restrict__ zs, int M, float variance,
-                                                       float inv_ls, int ldo, float* __restrict__ out) {
+                                                       float inv_ls, int ldo, float* __restrict__ out,
+                                                       const float* __restrict__ kscal = nullptr,
+                                                       __half* __restrict__ oh = nullptr, __half* __restrict__ ol = nullptr,
+                                                       long long Tpad = 0) {
   constexpr int LC = 32;
   __shared__ float Xs[LC][65];
   __shared__ float Zs[LC][65];
@@ -89,6 +95,28 @@ __global__ void __launch_bounds__(256) kuf_simt_kernel(const float* __restrict__
     }
     __syncthreads();
   }
+  if (LAYOUT == 2) {
+    const float ks = kscal[0];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long t = t0 + ty * 4 + u;
+      if (t >= Tpad) continue;
+      __half hi[4], lo[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int m = m0 + tx * 4 + w;
+        const float k = (t < T && m < M) ? ks * variance * expf(-0.5f * d[u][w]) : 0.f;
+        hi[w] = __float2half_rn(k);
+        lo[w] = __float2half_rn(k - __half2float(hi[w]));
+      }
+      const int m = m0 + tx * 4;
+      if (m < ldo) {   // ldo is a multiple of 64: the 4 columns are all inside; 8-byte vector stores
+        *reinterpret_cast<uint2*>(oh + t * ldo + m) = *reinterpret_cast<uint2*>(hi);
+        *reinterpret_cast<uint2*>(ol + t * ldo + m) = *reinterpret_cast<uint2*>(lo);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int t = t0 + ty * 4 + u;
@@ -119,6 +147,15 @@ int launch_kuf_simt(const float* X, const View& v, int n_rows, const float* zs, 
   else
     kuf_simt_kernel<0><<<grid, 256, 0, st>>>(X, v, T, n_rows, zs, M, variance, inv_ls, ldo, out);
   return check_launch("kuf_simt");
+}
+
+int launch_kuf_simt_planes(const float* X, const View& v, int n_rows, const float* zs, int M, float variance, float inv_ls,
+                           int ldo, const float* kscal, void* Kh, void* Kl, long long Tpad, cudaStream_t st) {
+  const int T = n_rows * v.P;
+  dim3 grid((unsigned)((Tpad + 63) / 64), ceil_div(ldo, 64));
+  kuf_simt_kernel<2><<<grid, 256, 0, st>>>(X, v, T, n_rows, zs, M, variance, inv_ls, ldo, nullptr, kscal, (__half*)Kh,
+                                          (__half*)Kl, Tpad);
+  return check_launch("kuf_simt_planes");
 }
 
 // [P,M,N] (reference Kuf layout) -> [N*P, ldo] rows t = n*P + p (conditional GEMM operand layout)

@@ -1,12 +1,565 @@
-// placeholder until the tcgen05 path lands
+// Tensor-core path (sm_100a): tcgen05.mma with TMEM accumulators, operands staged by TMA (SWIZZLE_128B) through an
+// mbarrier pipeline, warp-specialised (TMA producer / single-thread MMA issuer / 4 epilogue warps), persistent grid.
+//
+// K-D  `cond_tc_kernel`: the stacked conditional GEMM of SURVEY App. A.4
+//        G[t, j] = sum_m K[t, m] * W[j, m]        (t: patch-columns, j: (R+1)*Mp rows of W, m: inducing points)
+//      with the per-patch variance aggregation fused into the epilogue (acc[t, blk] = sum_{j in blk} G[t,j]^2 straight out
+//      of TMEM, so the reference's [R,M,P,N] tensor of conditionals.py:58 never exists), plus the mean rows.
+//      Precision: the reference is float64; fp16 tensor cores with fp32 accumulation are used through a 2-way operand split
+//      x = hi + lo (22 mantissa bits), G ~= Kh*Wh + Kh*Wl + Kl*Wh  -> three MMAs per k-step (lo*lo ~ 2^-22 dropped).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <string.h>
+
 #include "dcgp_tc.cuh"
+
 namespace dcgp {
-void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) { memset(&t, 0, sizeof(t)); t.bytes = 0; }
-int tc_pack_operands(const TcPrep&, const double*, int, const double*, const double*, int, int, int, cudaStream_t) { set_error("tc path not built"); return DCGP_ERR_ARG; }
-int tc_pack_z(const TcPrep&, const double*, int, int, double, cudaStream_t) { set_error("tc path not built"); return DCGP_ERR_ARG; }
-void tc_carve_cond(TcCondWork& w, int, int, int, size_t, void*) { memset(&w, 0, sizeof(w)); }
-int tc_split_rows(const float*, int, int, const TcCondWork&, cudaStream_t) { set_error("tc path not built"); return DCGP_ERR_ARG; }
-int tc_cond(const TcPrep&, const TcCondWork&, int, int, int, float*, float*, cudaStream_t) { set_error("tc path not built"); return DCGP_ERR_ARG; }
-void tc_carve_apply(TcApplyWork& a, int, int, int, int, int, size_t, size_t, void*) { memset(&a, 0, sizeof(a)); }
-int tc_layer_apply(const dcgp_layer_desc*, const View&, const TcPrep&, const TcApplyWork&, const double*, const float*, int, float*, float*, float*, float*, cudaStream_t) { set_error("tc path not built"); return DCGP_ERR_ARG; }
+
+// ============================================================================================ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; issued by ONE thread on behalf of the CTA.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i), columns [col, col+32).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, rows of 128 bytes (64 fp16), 8-row groups 1024 B apart
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;            // LBO: unused for swizzled K-major layouts
+  d |= (uint64_t)(1024 >> 4) << 32;  // SBO
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (InstrDescriptor in mma_sm100_desc.hpp): fp16 x fp16 -> fp32, both K-major, M=128, N=n.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4) /* c_format = F32 */ | (0u << 7) /* a = F16 */ | (0u << 10) /* b = F16 */ | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+// ============================================================================================ K-D kernel
+constexpr int kBM = 128;      // patch-columns per tile (UMMA M, TMEM lanes)
+constexpr int kBK = 64;       // inducing points per pipeline stage (one 128-byte swizzle atom of fp16)
+constexpr int kThreads = 192; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+template <int BN>
+struct CondCfg {
+  static constexpr int kStageA = kBM * kBK * 2;                 // one fp16 plane of the A tile
+  static constexpr int kStageB = BN * kBK * 2;                  // one fp16 plane of the B tile
+  static constexpr int kStageBytes = 2 * kStageA + 2 * kStageB; // hi+lo of both
+  static constexpr int kStages = (BN == 256) ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int kTmemCols = 2 * BN;                      // double-buffered accumulator
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct CondParams {
+  int T;          // valid patch-columns
+  int n_ttiles;   // ceil(T / 128)
+  int Mp;         // padded inducing points (multiple of 64)
+  int R;
+  int njt;        // Mp / BN  (j-tiles per row block)
+  int n_items;    // n_ttiles * (R + 2)
+  const float* wscal;  // device: [0]=W scale, [1]=1/W scale, [2]=Wmean scale, [3]=1/Wmean scale
+  const float* kscal;  // device: [0]=K scale, [1]=1/K scale
+  float* acc;     // [T, R+1]
+  float* mean;    // [T, R]
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+cond_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, CondParams p) {
+  using Cfg = CondCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-B alignment
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;             // [2]
+  uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = p.Mp / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
+        const int njt = (blk == p.R + 1) ? 1 : p.njt;
+        for (int jt = 0; jt < njt; ++jt) {
+          const int brow = blk * p.Mp + jt * BN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(st, &tmA_hi, &full_bar[stage], kb * kBK, tt * kBM);
+            tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, tt * kBM);
+            tma_load_2d(st + 2 * Cfg::kStageA, &tmB_hi, &full_bar[stage], kb * kBK, brow);
+            tma_load_2d(st + 2 * Cfg::kStageA + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb * kBK, brow);
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BN);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t tile = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
+        const int njt = (blk == p.R + 1) ? 1 : p.njt;
+        for (int jt = 0; jt < njt; ++jt, ++tile) {
+          const uint32_t buf = tile & 1, use = tile >> 1;
+          mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t a_lo = a_hi + Cfg::kStageA;
+            const uint32_t b_hi = a_hi + 2 * Cfg::kStageA;
+            const uint32_t b_lo = b_hi + Cfg::kStageB;
+            const uint64_t dah = make_sw128_desc(a_hi), dal = make_sw128_desc(a_lo);
+            const uint64_t dbh = make_sw128_desc(b_hi), dbl = make_sw128_desc(b_lo);
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // advance 32 bytes inside the swizzle atom
+              // small cross terms first, dominant term last
+              umma_f16(d_tmem, dal + koff, dbh + koff, idesc, (kb | k) != 0);
+              umma_f16(d_tmem, dah + koff, dbl + koff, idesc, 1);
+              umma_f16(d_tmem, dah + koff, dbh + koff, idesc, 1);
+            }
+            umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tmem_full[buf]);                     // accumulator complete -> epilogue
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 4 warps <-> 4 TMEM lane quarters
+    const int q = warp & 3;                                  // warps 2,3,4,5 -> quarters 2,3,0,1
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float inv_w = p.wscal[1], inv_wm = p.wscal[3], inv_k = p.kscal[1];
+    const float sq_scale = (inv_w * inv_k) * (inv_w * inv_k);
+    const float mean_scale = inv_wm * inv_k;
+    uint32_t tile = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
+      const bool is_mean = (blk == p.R + 1);
+      const int njt = is_mean ? 1 : p.njt;
+      const int t = tt * kBM + q * 32 + lane;
+      float ssq = 0.f;
+      for (int jt = 0; jt < njt; ++jt, ++tile) {
+        const uint32_t buf = tile & 1, use = tile >> 1;
+        mbar_wait(&tmem_full[buf], use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + lane_base + buf * BN;
+        if (is_mean) {
+          float v[32];
+          tmem_ld_32x32(taddr, v);
+          if (t < p.T) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < p.R) p.mean[(long long)t * p.R + r] = v[r] * mean_scale;
+          }
+          if (p.R > 32) {
+            tmem_ld_32x32(taddr + 32, v);
+            if (t < p.T) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r)
+                if (32 + r < p.R) p.mean[(long long)t * p.R + 32 + r] = v[r] * mean_scale;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld_32x32(taddr + c, v);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+              s2 = fmaf(v[i + 2], v[i + 2], s2); s3 = fmaf(v[i + 3], v[i + 3], s3);
+            }
+            ssq += (s0 + s1) + (s2 + s3);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
+      }
+      if (!is_mean && t < p.T) p.acc[(long long)t * (p.R + 1) + blk] = ssq * sq_scale;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ============================================================================================ host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+// 2-D fp16 row-major [rows, cols] tensor, box = [box_rows, 64 cols] (128 bytes inner), SWIZZLE_128B.
+static int make_tmap_f16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return DCGP_ERR_CUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%u", (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows); return DCGP_ERR_CUDA; }
+  return DCGP_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr int kWPadRows = 256;   // zero rows after the mean block so a BN-row box never leaves the tensor
+
+static size_t w_rows(int Mp, int R) { return (size_t)(R + 1) * Mp + kWPadRows; }
+
+template <int BN>
+static int launch_cond_tc(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st) {
+  using Cfg = CondCfg<BN>;
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  int rc;
+  if ((rc = make_tmap_f16(&tmAh, w.Kh, w.Tpad, Mp, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmAl, w.Kl, w.Tpad, Mp, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmBh, prep.Wh, w_rows(Mp, R), Mp, BN))) return rc;
+  if ((rc = make_tmap_f16(&tmBl, prep.Wl, w_rows(Mp, R), Mp, BN))) return rc;
+  CondParams p;
+  p.T = T; p.n_ttiles = ceil_div(T, kBM); p.Mp = Mp; p.R = R; p.njt = Mp / BN;
+  p.n_items = p.n_ttiles * (R + 2);
+  p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(cond_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("cond_tc smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
+    attr = true;
+  }
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  cond_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmAh, tmAl, tmBh, tmBl, p);
+  return check_launch("cond_tc");
+}
+
+int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st) {
+  if (R > 64) { set_error("tc_cond: R > 64 unsupported"); return DCGP_ERR_ARG; }
+  if (Mp % 256 == 0) return launch_cond_tc<256>(prep, w, T, Mp, R, acc, mean, st);
+  if (Mp % 128 == 0) return launch_cond_tc<128>(prep, w, T, Mp, R, acc, mean, st);
+  return launch_cond_tc<64>(prep, w, T, Mp, R, acc, mean, st);
+}
+
+// ============================================================================================ operand splitting
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+// max |x| over a float64 array -> power-of-two scale that maps it to [2^13, 2^14)  (fp16 max is 65504).
+__global__ void __launch_bounds__(1024) scale_from_max_f64_kernel(const double* __restrict__ a, long long na, int lda, int cols,
+                                                                  const double* __restrict__ b, long long nb,
+                                                                  float* __restrict__ scal2) {
+  __shared__ double sh[32];
+  double m = 0.0;
+  for (long long e = threadIdx.x; e < na; e += 1024) {
+    const long long r = e / cols;
+    const int c = (int)(e % cols);
+    m = fmax(m, fabs(a[r * lda + c]));
+  }
+  for (long long e = threadIdx.x; e < nb; e += 1024) m = fmax(m, fabs(b[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 32; ++i) m = fmax(m, sh[i]);
+    int e = 0;
+    if (m > 0.0 && isfinite(m)) { frexp(m, &e); }   // m = f * 2^e, f in [0.5, 1)
+    const float s = ldexpf(1.f, 14 - e);
+    scal2[0] = s;
+    scal2[1] = 1.f / s;
+  }
+}
+__global__ void __launch_bounds__(1024) scale_from_max_f32_kernel(const float* __restrict__ a, long long n, float* __restrict__ scal2) {
+  __shared__ float sh[32];
+  float m = 0.f;
+  for (long long e = threadIdx.x; e < n; e += 1024) m = fmaxf(m, fabsf(a[e]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 32; ++i) m = fmaxf(m, sh[i]);
+    int e = 0;
+    if (m > 0.f && isfinite(m)) { frexpf(m, &e); }
+    const float s = ldexpf(1.f, 14 - e);
+    scal2[0] = s;
+    scal2[1] = 1.f / s;
+  }
+}
+__global__ void set_scale_kernel(float bound, float* __restrict__ scal2) {
+  int e = 0;
+  frexpf(bound, &e);
+  const float s = ldexpf(1.f, 14 - e);
+  scal2[0] = s;
+  scal2[1] = 1.f / s;
+}
+
+// W planes: rows [0, (R+1)*Mp) = blocks (block 0 = Linv, block r = Wr[r-1]), then the mean rows (beta^T), then zero padding.
+__global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, const double* __restrict__ Wr,
+                                  const double* __restrict__ beta, int M, int Mp, int R, long long rows_total,
+                                  const float* __restrict__ scal, __half* __restrict__ Wh, __half* __restrict__ Wl) {
+  const double sw = (double)scal[0], swm = (double)scal[2];
+  const long long total = rows_total * Mp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(e % Mp);
+    const long long row = e / Mp;
+    double v = 0.0;
+    if (j < M) {
+      if (row < (long long)(R + 1) * Mp) {
+        const int blk = (int)(row / Mp), i = (int)(row % Mp);
+        if (i < M) v = sw * ((blk == 0) ? Linv[(long long)i * ldl + j] : Wr[((long long)(blk - 1) * M + i) * M + j]);
+      } else {
+        const int r = (int)(row - (long long)(R + 1) * Mp);
+        if (r < R) v = swm * beta[(long long)j * R + r];
+      }
+    }
+    const float x = (float)v;
+    __half hi = __float2half_rn(x);
+    // the low part is taken from the float64 value so that hi + lo carries 22 bits of the original
+    __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
+    Wh[e] = hi;
+    Wl[e] = lo;
+  }
+}
+
+__global__ void split_rows_kernel(const float* __restrict__ Kt, long long T, int Mp, long long Tpad, const float* __restrict__ kscal,
+                                  __half* __restrict__ Kh, __half* __restrict__ Kl) {
+  const float s = kscal[0];
+  const long long total = Tpad * Mp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long t = e / Mp;
+    const float x = (t < T) ? Kt[e] * s : 0.f;
+    __half hi, lo;
+    split_f16(x, hi, lo);
+    Kh[e] = hi;
+    Kl[e] = lo;
+  }
+}
+
+// ============================================================================================ host plumbing
+struct Carve2 {
+  char* base; size_t off = 0;
+  explicit Carve2(void* p) : base((char*)p) {}
+  void* take(size_t bytes) {
+    off = align_up(off, 1024);
+    void* r = base ? base + off : nullptr;
+    off += bytes;
+    return r;
+  }
+};
+
+void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
+  memset(&t, 0, sizeof(t));
+  t.M = M; t.Mp = Mp; t.R = R; t.L = L; t.Lp = (int)align_up(L, 64);
+  Carve2 c(buf);
+  const size_t wbytes = w_rows(Mp, R) * Mp * 2;
+  t.Wh = c.take(wbytes);
+  t.Wl = c.take(wbytes);
+  t.Zh = c.take((size_t)Mp * t.Lp * 2);
+  t.Zl = c.take((size_t)Mp * t.Lp * 2);
+  t.zz = (float*)c.take((size_t)Mp * 4);
+  t.scal = (float*)c.take(8 * 4);
+  t.Wmh = t.Wml = nullptr;
+  t.bytes = align_up(c.off, 1024);
+}
+
+int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double* Wr, const double* beta, int M, int Mp, int R,
+                     cudaStream_t st) {
+  // scale of the variance blocks: max over Linv (M x M, ld ldl) and Wr (R*M*M contiguous); of the mean rows: max over beta
+  scale_from_max_f64_kernel<<<1, 1024, 0, st>>>(Linv, (long long)M * M, ldl, M, Wr, (long long)R * M * M, t.scal + 0);
+  scale_from_max_f64_kernel<<<1, 1024, 0, st>>>(beta, (long long)M * R, R, R, nullptr, 0, t.scal + 2);
+  pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, Wr, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal, (__half*)t.Wh,
+                                                   (__half*)t.Wl);
+  return check_launch("tc_pack_operands");
+}
+
+int tc_pack_z(const TcPrep&, const double*, int, int, double, cudaStream_t) { return DCGP_OK; }  // used by the tensor-core Kuf kernel
+
+void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf) {
+  memset(&w, 0, sizeof(w));
+  w.Tpad = align_up(T, kBM);
+  Carve2 c(buf);
+  w.Kh = c.take(w.Tpad * Mp * 2);
+  w.Kl = c.take(w.Tpad * Mp * 2);
+  w.kscal = (float*)c.take(8 * 4);
+  void* prep_buf = c.take(0);
+  tc_carve_prep(w.prep, M, Mp, R, 1, prep_buf);
+  c.off += w.prep.bytes;
+  w.bytes = align_up(c.off, 1024);
+}
+
+int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStream_t st) {
+  scale_from_max_f32_kernel<<<1, 1024, 0, st>>>(Kt, (long long)T * Mp, w.kscal);
+  split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(Kt, T, Mp, (long long)w.Tpad, w.kscal, (__half*)w.Kh, (__half*)w.Kl);
+  return check_launch("tc_split_rows");
+}
+
+void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, void* buf) {
+  memset(&a, 0, sizeof(a));
+  Carve2 c(buf);
+  // conv: the Kuf kernel writes fp16 planes of the [Tk, Mp] kernel matrix directly.
+  // svgp: the patch-level matrix stays fp32 (it is averaged over patches first); only Kzx [T, Mp] is split.
+  const size_t rows = (kind == DCGP_LAYER_CONV) ? Tk : T;
+  a.kk.Tpad = align_up(rows, kBM);
+  a.kk.Kh = c.take(a.kk.Tpad * Mp * 2);
+  a.kk.Kl = c.take(a.kk.Tpad * Mp * 2);
+  a.kk.kscal = (float*)c.take(8 * 4);
+  a.bytes = align_up(c.off, 1024);
+}
+
+int launch_kuf_simt_planes(const float* X, const View& v, int n_rows, const float* zs, int M, float variance, float inv_ls,
+                           int ldo, const float* kscal, void* Kh, void* Kl, long long Tpad, cudaStream_t st);
+
+int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const float* zs,
+                   float* Kt32, const double* patch_weights, const float* X, int n_rows, float* Kzx, float* acc, float* mean_t,
+                   cudaStream_t st) {
+  const int Mp = prep.Mp, M = prep.M, R = prep.R;
+  const float variance = (float)d->variance, inv_ls = (float)(1.0 / d->lengthscale);
+  if (d->kind == DCGP_LAYER_CONV) {
+    const int T = n_rows * v.P;
+    set_scale_kernel<<<1, 1, 0, st>>>(variance, a.kk.kscal);      // RBF values lie in (0, variance]
+    int rc = launch_kuf_simt_planes(X, v, n_rows, zs, M, variance, inv_ls, Mp, a.kk.kscal, a.kk.Kh, a.kk.Kl, (long long)a.kk.Tpad, st);
+    if (rc) return rc;
+    return tc_cond(prep, a.kk, T, Mp, R, acc, mean_t, st);
+  }
+  int rc = launch_kuf_simt(X, v, n_rows, zs, M, variance, inv_ls, 1, Mp, Kt32, st);
+  if (rc) return rc;
+  rc = launch_patch_mean(Kt32, n_rows, v.P, Mp, M, patch_weights, 0, Mp, Kzx, st);
+  if (rc) return rc;
+  rc = tc_split_rows(Kzx, n_rows, Mp, a.kk, st);
+  if (rc) return rc;
+  return tc_cond(prep, a.kk, n_rows, Mp, R, acc, mean_t, st);
+}
+
+}  // namespace dcgp

@@ -22,8 +22,9 @@ int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double*
 int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st);
 
 struct TcCondWork {
-  TcPrep prep;
+  TcPrep prep;    // only carved by tc_carve_cond (the conditional() API mirror owns its operands)
   void *Kh, *Kl;  // [Tpad, Mp] fp16 planes of the kernel-matrix rows
+  float* kscal;   // device: [0] = K scale, [1] = 1 / K scale
   size_t Tpad;
   size_t bytes;
 };
@@ -32,14 +33,12 @@ int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStrea
 int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st);
 
 struct TcApplyWork {
-  TcCondWork kk;   // planes for the patch-level kernel matrix (Tk rows)
-  TcCondWork kz;   // planes for the image-level Kzx (SVGP_CONV only)
-  float* Kt32;     // [Tk, Mp] fp32 staging (SVGP_CONV patch-mean input)
+  TcCondWork kk;   // planes of the matrix the conditional GEMM consumes (Kuf rows for conv, Kzx rows for svgp)
   size_t bytes;
 };
 void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, void* buf);
-int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a,
-                   const double* patch_weights, const float* X, int n_rows, float* Kzx, float* kdiag, float* acc,
+int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const float* zs,
+                   float* Kt32, const double* patch_weights, const float* X, int n_rows, float* Kzx, float* acc,
                    float* mean_t, cudaStream_t st);
 
 }  // namespace dcgp

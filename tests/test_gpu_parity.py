@@ -229,9 +229,10 @@ def test_varexp_matches_oracle_on_random_inputs():
 def _synthetic_conv(rng, H, W, C, f, s, M, R, white=False, trained=True):
     from oracle import dcgp_oracle as O
     L = f * f * C
-    Ximg = rng.standard_normal((16, H, W, C))
+    P = ((H - f) // s + 1) * ((W - f) // s + 1)
+    Ximg = rng.standard_normal((max(16, 2 * M // P + 1), H, W, C))      # enough distinct patches for M inducing points
     pat = O.extract_patches(Ximg, f, s).reshape(-1, L)
-    Z = pat[rng.choice(pat.shape[0], M, replace=pat.shape[0] < M)] + 0.1 * rng.standard_normal((M, L))
+    Z = pat[rng.choice(pat.shape[0], M, replace=False)] + 0.1 * rng.standard_normal((M, L))
     lay = dict(type="conv", H=H, W=W, C=C, f=f, s=s, M=M, R=R, white=white, variance=5.0, lengthscale=5.0, Z=Z)
     if trained:
         lay["q_mu"] = rng.standard_normal((M, R))
