@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- ELBO-step images/sec for the 3-layer CIFAR-10 DCGP (M=512, 5x5 patches, batch 256/GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); rank 0 prints ONE JSON line.
+Workload (BASELINE.json configs[2]): 32x32x3 synthetic images, ConvLayer(f=5,s=2,M=512,R=10) ->
+ConvLayer(f=5,s=1,M=512,R=10) -> SVGP(ConvKernel f=5,s=1,M=512,10 classes), S=10, sigma^2=5, l=5, jitter=1e-3,
+non-white, trained-like variational state.  Images shard over ranks (weak scaling: 256 images per GPU).
+
+A "step" is what the library implements of the ELBO step today -- see `config.step` in the JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (H, W, C, [(f, s, M, R) conv layers], (f, s, M) last layer, batch per GPU, S)
+    "cfg2": dict(H=28, W=28, C=1, conv=[(5, 2, 128, 10)], last=(5, 1, 128), batch=128, S=10,
+                 desc="MNIST 2-layer DCGP M=128 batch 128"),
+    "cfg3": dict(H=32, W=32, C=3, conv=[(5, 2, 512, 10), (5, 1, 512, 10)], last=(5, 1, 512), batch=256, S=10,
+                 desc="CIFAR-10 3-layer DCGP M=512 batch 256"),
+    "cfg4": dict(H=32, W=32, C=3, conv=[(5, 2, 1024, 10), (5, 1, 1024, 10)], last=(5, 1, 1024), batch=64, S=10,
+                 desc="CIFAR-10 3-layer DCGP M=1024 batch 512 over 8 GPUs (64/GPU)"),
+}
+NUM_DATA = 50000
+SIGMA2, LENGTHSCALE, JITTER = 5.0, 5.0, 1e-3
+
+
+# ----------------------------------------------------------------------------------------------- synthetic model
+def synth_params(cfg, seed=1236):
+    """Seeded synthetic parameters: Z = patches sampled from N(0,1) inputs of the layer's shape + N(0,0.1^2);
+    trained-like q: q_mu ~ N(0,1), q_sqrt = tril(N(0,0.3^2)) + 0.5 I.  Pure numpy, identical on every rank."""
+    rng = np.random.RandomState(seed)
+    layers = []
+    h, w, c = cfg["H"], cfg["W"], cfg["C"]
+    specs = [(f, s, M, R, "conv") for (f, s, M, R) in cfg["conv"]] + [cfg["last"] + (10, "svgp_conv")]
+    for (f, s, M, R, kind) in specs:
+        L = f * f * c
+        oh, ow = (h - f) // s + 1, (w - f) // s + 1
+        nimg = max(8, 2 * M // (oh * ow) + 1)
+        img = rng.standard_normal((nimg, h, w, c))
+        Z = np.empty((M, L))
+        for i in range(M):
+            n, y, x = rng.randint(nimg), rng.randint(h - f + 1), rng.randint(w - f + 1)
+            Z[i] = img[n, y:y + f, x:x + f, :].reshape(-1)
+        Z += 0.1 * rng.standard_normal((M, L))
+        lay = dict(type=kind, H=h, W=w, C=c, f=f, s=s, M=M, R=R, white=False, variance=SIGMA2, lengthscale=LENGTHSCALE,
+                   Z=Z, q_mu=rng.standard_normal((M, R)),
+                   q_sqrt=np.tril(rng.standard_normal((R, M, M)) * 0.3) + 0.5 * np.eye(M))
+        if kind == "svgp_conv":
+            lay["patch_weights"] = np.ones(oh * ow)
+        layers.append(lay)
+        h, w, c = oh, ow, R
+    return layers
+
+
+def build_model(layers, S, device):
+    import deepcgp_b200 as D
+    built = []
+    for lay in layers:
+        kern = D.RBF(lay["f"] ** 2 * lay["C"], variance=lay["variance"], lengthscales=lay["lengthscale"])
+        feat = D.PatchInducingFeatures(lay["Z"])
+        if lay["type"] == "conv":
+            view = D.FullView((lay["H"], lay["W"]), lay["f"], lay["C"], lay["s"])
+            built.append(D.ConvLayer(kern, D.Zero(), feature=feat, view=view, white=lay["white"], gp_count=lay["R"],
+                                     q_mu=lay["q_mu"], q_sqrt=lay["q_sqrt"], device=device))
+        else:
+            view = D.FullView((lay["H"], lay["W"], lay["C"]), lay["f"], lay["C"], lay["s"])
+            built.append(D.SVGP_Layer(D.ConvKernel(kern, view, lay["patch_weights"]), lay["R"], D.Zero(lay["R"]),
+                                      feature=feat, white=lay["white"], q_mu=lay["q_mu"], q_sqrt=lay["q_sqrt"],
+                                      device=device))
+    return D.DGP_Base(np.zeros((1, 1), np.float32), np.zeros((1, 1)), D.MultiClass(10), built, num_samples=S,
+                      num_data=NUM_DATA, device=device)
+
+
+def algorithmic_flops(cfg, n_img):
+    """SURVEY.md 8d canonical forward flops per step (per GPU), and the share of the conditional-GEMM kernel."""
+    S = cfg["S"]
+    h, w, c = cfg["H"], cfg["W"], cfg["C"]
+    total, cond_layers = 0.0, []
+    specs = [(f, s, M, R, "conv") for (f, s, M, R) in cfg["conv"]] + [cfg["last"] + (10, "svgp_conv")]
+    for i, (f, s, M, R, kind) in enumerate(specs):
+        L = f * f * c
+        oh, ow = (h - f) // s + 1, (w - f) // s + 1
+        P = oh * ow
+        n_eff = n_img if i == 0 else S * n_img
+        f_m = 2.0 * M * M * L + M ** 3 / 3.0 + R * M ** 3 / 3.0 + M * M * R
+        if kind == "conv":
+            T = P * n_eff
+            cond = T * (M * M + 2.0 * M * R + R * M * M + 2.0 * M * (R + 1))
+            total += T * 2.0 * M * L + cond + f_m
+        else:
+            T = n_eff
+            cond = T * (M * M + 2.0 * M * R + R * M * M)
+            total += n_eff * (2.0 * M * L * P + 2.0 * L * P * P) + cond + f_m
+        cond_layers.append(cond)
+        h, w, c = oh, ow, R
+    return total, cond_layers
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference_rate(cfg, layers, n_img, seed=99):
+    """The reference's CPU implementation cannot run here (TensorFlow/GPflow absent): the float64
+    oracle restatement (oracle/dcgp_oracle.py, single-solve form, all host BLAS threads) is timed on a bounded sample of
+    the same workload: `n_img` images with all S samples each, full 3-layer forward ELBO."""
+    from oracle import dcgp_oracle as O
+    rng = np.random.RandomState(seed)
+    S = cfg["S"]
+    X = rng.standard_normal((n_img, cfg["H"] * cfg["W"] * cfg["C"]))
+    Y = rng.randint(0, 10, size=(n_img, 1))
+    zs = []
+    for lay in layers:
+        oh, ow = O.out_image_size(lay["H"], lay["W"], lay["f"], lay["s"])
+        D = oh * ow * lay["R"] if lay["type"] == "conv" else lay["R"]
+        zs.append(rng.standard_normal((S, n_img, D)))
+    t0 = time.perf_counter()
+    elbo = O.dgp_elbo(layers, X, Y, zs, NUM_DATA, S, JITTER, fast=True)
+    dt = time.perf_counter() - t0
+    return n_img / dt, dt, float(elbo)
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    layers = synth_params(cfg)
+    n_img = args.ref_images
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, dt, _ = cpu_reference_rate(cfg, layers, n_img, seed=99 + i)
+        if i >= args.warmup:
+            rates.append((r, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([dt for _, dt in rates])) * 1e3
+    cores = os.cpu_count()
+    sample = "%d images x S=%d, full 3-layer forward ELBO, float64 NumPy/SciPy oracle port (TF/GPflow not installable)" % (n_img, cfg["S"])
+    line = {"impl": "reference", "metric": "ELBO-step images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.config + ": " + cfg["desc"], "step": "forward ELBO (CPU oracle port)", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args, cfg):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from deepcgp_b200 import _lib
+
+    S, B = cfg["S"], cfg["batch"]
+    n_global = B * world
+    layers = synth_params(cfg)
+    model = build_model(layers, S, device)
+    rng = np.random.RandomState(4321 + rank)
+    D_in = cfg["H"] * cfg["W"] * cfg["C"]
+    n_batches = 4                                        # rotate distinct host batches (pinned), like a data loader
+    hostX = [torch.from_numpy(rng.standard_normal((B, D_in)).astype(np.float32)).pin_memory() for _ in range(n_batches)]
+    hostY = [torch.from_numpy(rng.randint(0, 10, size=(B,)).astype(np.int32)).pin_memory() for _ in range(n_batches)]
+    devX = [x.to(device) for x in hostX]
+    devY = [y.to(device) for y in hostY]
+    gen = torch.Generator(device=device).manual_seed(777 + rank)
+    dims = [l.num_outputs for l in model.layers]
+    zs = [torch.randn((S, B, d), device=device, generator=gen) for d in dims]   # fixed N(0,1) draws, resident in HBM
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
+    elbo_host = torch.empty(1, dtype=torch.float64).pin_memory()
+
+    def step_resident(i):
+        return model._build_likelihood(devX[i % n_batches], devY[i % n_batches], zs=zs, n_global=n_global)
+
+    def step_e2e(i):
+        x = hostX[i % n_batches].to(device, non_blocking=True)
+        y = hostY[i % n_batches].to(device, non_blocking=True)
+        e = model._build_likelihood(x, y, zs=zs, n_global=n_global)
+        elbo_host.copy_(e.reshape(1), non_blocking=True)
+        return e
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        torch.cuda.synchronize()
+        for i in range(steps):
+            flush.zero_()                                # L2 flush between timed iterations (not timed)
+            ev[i][0].record()
+            step_fn(i)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)    # device time, max over ranks
+        return float(ms.item()) / steps
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib.dcgp_launch_count()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    launches = _lib.lib.dcgp_launch_count() - launches0
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    for layer in model.layers:
+        _lib.raise_if_not_pd(layer._info)
+    elbo_val = float(model._elbo.item())
+
+    # roofline of the dominant kernel (the tcgen05 conditional GEMM of layer 2), timed live with CUDA events
+    roof = None
+    if rank == 0:
+        roof = kernel_roofline(model, cfg, B, S, device, flush)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r, dt, _ = cpu_reference_rate(cfg, layers, args.ref_images)
+        cpu = {"value": r, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d images x S=%d, full 3-layer forward ELBO in %.1f s, float64 NumPy/SciPy oracle port "
+                         "(reference TF/GPflow path not installable)" % (args.ref_images, S, dt)}
+    total_flops, _ = algorithmic_flops(cfg, B)
+    line = {"metric": "ELBO-step images/sec", "value": n_global / (ms_res * 1e-3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp16x2-split tensor cores (fp32 accumulate) + f64 M-only", "data": "synthetic",
+            "config": {"workload": args.config + ": " + cfg["desc"], "step": "forward ELBO (a1-a9); backward+Adam not built yet",
+                       "images_per_gpu": B, "num_samples": S, "l2_flush": "256 MiB buffer written between timed steps",
+                       "algorithmic_gflop_per_step_per_gpu": total_flops / 1e9, "elbo": elbo_val},
+            "e2e": {"value": n_global / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": B * D_in * 4 + B * 4, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(model, cfg, B, S, device, flush):
+    """Dominant kernel = cond_tc_kernel of conv layer 2 (81% of the step's flops).  Times dcgp_layer_apply pieces live:
+    the conditional GEMM alone is isolated by timing apply with and without it is not possible through the C ABI, so
+    the layer-2 apply (Kuf + conditional GEMM + finalize) is timed and the share of the GEMM comes from the committed
+    ncu launch list (profiles/)."""
+    import torch
+    if len(model.layers) < 3:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    layer = model.layers[1]
+    n_rows = S * B
+    D_in = int(np.prod(layer.view.input_size)) * layer.view.feature_maps
+    X = torch.randn((n_rows, D_in), device=device)
+    layer.prepare()
+    layer._hold = True
+    for _ in range(3):
+        layer._conditional(X)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        layer._conditional(X)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    layer._hold = False
+    ms = float(np.mean(ts))
+    _, cond = algorithmic_flops(cfg, B)
+    M, R, P = layer.num_inducing, layer.gp_count, layer.patch_count
+    L = layer.patch_length
+    T = P * n_rows
+    alg = cond[1] + T * 2.0 * M * L          # conditional GEMM + Kuf of this layer (what the timed region runs)
+    executed = 3 * 2.0 * T * ((R + 1) * M * M + 256 * M)
+    ach = alg / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "layer-2 apply: kuf + cond_tc_kernel<256> + finalize", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms": ms, "algorithmic_gflop": alg / 1e9,
+            "executed_tensor_gflop": executed / 1e9, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--ref-images", type=int, default=32, help="images in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -58,7 +58,7 @@ static Prep carve_prep(const dcgp_layer_desc* d, void* buf) {
 
 struct F64Work {
   int M, Mq, R;
-  double *Kuu, *invD, *Linv, *Kinv, *Wr, *beta, *Lpinv, *invDp, *tmpMR, *sc;
+  double *Kuu, *invD, *Linv, *Kinv, *Wr, *beta, *Lpinv, *invDp, *tmpMR, *tmpK, *sc;
   void* trws;
   size_t bytes;
 };
@@ -79,6 +79,7 @@ static F64Work carve_f64(int M, int R, void* ws) {
   w.Lpinv = c.take<double>((size_t)w.Mq * w.Mq);
   w.invDp = c.take<double>(potrf_ws_bytes(M) / sizeof(double));
   w.tmpMR = c.take<double>((size_t)M * R);
+  w.tmpK = c.take<double>((size_t)M * M);
   w.sc = c.take<double>(8);
   w.bytes = align_up(c.off, 256);
   return w;
@@ -87,13 +88,14 @@ static F64Work carve_f64(int M, int R, void* ws) {
 // Kuu (in w.Kuu) -> Lm (in place), Lm^-1, and the stacked conditional operand:
 //   non-white: G = Kuu^-1,  W_r = L_r^T G (= C_r^T Lm^-1, C_r = Lm^-1 L_r),  beta = G q_mu        (conditionals.py:44-58)
 //   white    : G = Lm^-1,   W_r = L_r^T G,                                   beta = G^T q_mu
-static int build_operands(const F64Work& w, int white, const double* q_mu, const double* q_sqrt, int* info,
-                          cudaStream_t st) {
+struct GInfo { const double* G; int ldg; };
+
+static int factor_and_G(const F64Work& w, int white, const double* q_mu, int* info, GInfo* gi, cudaStream_t st) {
   const int M = w.M, R = w.R, Mq = w.Mq;
   DCGP_TRY(potrf_f64(w.Kuu, M, M, w.invD, info, st));
   DCGP_TRY(trtri_f64(w.Kuu, M, M, w.invD, w.Linv, w.trws, st));
-  const double* G = w.Linv;
-  int ldg = Mq;
+  gi->G = w.Linv;
+  gi->ldg = Mq;
   if (!white) {
     GemmF64 g{};
     g.m = g.n = g.k = M;
@@ -101,33 +103,39 @@ static int build_operands(const F64Work& w, int white, const double* q_mu, const
     g.B = w.Linv; g.ldb = Mq; g.lowerB = 1;
     g.C = w.Kinv; g.ldc = M; g.alpha = 1.0; g.batch = 1;
     DCGP_TRY(gemm_f64(g, st));
-    G = w.Kinv;
-    ldg = M;
+    gi->G = w.Kinv;
+    gi->ldg = M;
   }
-  {
-    GemmF64 g{};  // W_r = L_r^T G
-    g.m = g.n = g.k = M;
-    g.A = q_sqrt; g.lda = M; g.transA = 1; g.lowerA = 1; g.strideA = (long long)M * M;
-    g.B = G; g.ldb = ldg; g.lowerB = white ? 1 : 0; g.strideB = 0;
-    g.C = w.Wr; g.ldc = M; g.strideC = (long long)M * M;
-    g.alpha = 1.0; g.batch = R;
-    DCGP_TRY(gemm_f64(g, st));
-  }
-  {
-    GemmF64 g{};  // beta = G^T q_mu
-    g.m = M; g.n = R; g.k = M;
-    g.A = G; g.lda = ldg; g.transA = 1; g.lowerA = white ? 1 : 0;
-    g.B = q_mu; g.ldb = R;
-    g.C = w.beta; g.ldc = R; g.alpha = 1.0; g.batch = 1;
-    DCGP_TRY(gemm_f64(g, st));
-  }
-  return DCGP_OK;
+  GemmF64 g{};  // beta = G^T q_mu
+  g.m = M; g.n = R; g.k = M;
+  g.A = gi->G; g.lda = gi->ldg; g.transA = 1; g.lowerA = white ? 1 : 0;
+  g.B = q_mu; g.ldb = R;
+  g.C = w.beta; g.ldc = R; g.alpha = 1.0; g.batch = 1;
+  return gemm_f64(g, st);
+}
+
+static int wr_f64(const F64Work& w, int white, const GInfo& gi, const double* q_sqrt, cudaStream_t st) {
+  const int M = w.M, R = w.R;
+  GemmF64 g{};  // W_r = L_r^T G
+  g.m = g.n = g.k = M;
+  g.A = q_sqrt; g.lda = M; g.transA = 1; g.lowerA = 1; g.strideA = (long long)M * M;
+  g.B = gi.G; g.ldb = gi.ldg; g.lowerB = white ? 1 : 0; g.strideB = 0;
+  g.C = w.Wr; g.ldc = M; g.strideC = (long long)M * M;
+  g.alpha = 1.0; g.batch = R;
+  return gemm_f64(g, st);
+}
+
+static int build_operands(const F64Work& w, int white, const double* q_mu, const double* q_sqrt, int* info,
+                          cudaStream_t st) {
+  GInfo gi;
+  DCGP_TRY(factor_and_G(w, white, q_mu, info, &gi, st));
+  return wr_f64(w, white, gi, q_sqrt, st);
 }
 
 // KL[q(u) || p(u)]: GPflow gauss_kl (layers.py:145-147) == the hand-written DS/layers.py:242-256.
 // Lp/Lpinv: Cholesky factor of the prior covariance and its inverse (ignored when white).
 static int kl_terms(const F64Work& w, int white, const double* Lp, int ldp, const double* Lpinv, int ldpi,
-                    const double* q_mu, const double* q_sqrt, double* kl, cudaStream_t st) {
+                    const double* q_mu, const double* q_sqrt, double* kl, cudaStream_t st, bool have_trace = false) {
   const int M = w.M, R = w.R;
   if (white) {
     DCGP_TRY(sumsq_f64(q_mu, M, R, R, 0, w.sc + 0, st));
@@ -140,14 +148,16 @@ static int kl_terms(const F64Work& w, int white, const double* Lp, int ldp, cons
     g.C = w.tmpMR; g.ldc = R; g.alpha = 1.0; g.batch = 1;
     DCGP_TRY(gemm_f64(g, st));
     DCGP_TRY(sumsq_f64(w.tmpMR, M, R, R, 0, w.sc + 0, st));
-    GemmF64 h{};  // Lp^-1 L_r
-    h.m = h.n = h.k = M;
-    h.A = Lpinv; h.lda = ldpi; h.lowerA = 1; h.strideA = 0;
-    h.B = q_sqrt; h.ldb = M; h.lowerB = 1; h.strideB = (long long)M * M;
-    h.C = w.Wr; h.ldc = M; h.strideC = (long long)M * M;
-    h.alpha = 1.0; h.batch = R;
-    DCGP_TRY(gemm_f64(h, st));
-    DCGP_TRY(sumsq_f64(w.Wr, (long long)R * M, M, M, 0, w.sc + 1, st));
+    if (!have_trace) {   // (the tensor-core path has already accumulated the trace into sc[1])
+      GemmF64 h{};  // Lp^-1 L_r
+      h.m = h.n = h.k = M;
+      h.A = Lpinv; h.lda = ldpi; h.lowerA = 1; h.strideA = 0;
+      h.B = q_sqrt; h.ldb = M; h.lowerB = 1; h.strideB = (long long)M * M;
+      h.C = w.Wr; h.ldc = M; h.strideC = (long long)M * M;
+      h.alpha = 1.0; h.batch = R;
+      DCGP_TRY(gemm_f64(h, st));
+      DCGP_TRY(sumsq_f64(w.Wr, (long long)R * M, M, M, 0, w.sc + 1, st));
+    }
     DCGP_TRY(logdiag2_f64(Lp, ldp, M, 1, 0, w.sc + 3, st));
   }
   DCGP_TRY(logdiag2_f64(q_sqrt, M, M, R, (long long)M * M, w.sc + 2, st));
@@ -171,6 +181,7 @@ extern "C" {
 
 const char* dcgp_last_error(void) { return dcgp::last_error(); }
 int dcgp_version(void) { return 100; }
+long long dcgp_launch_count(void) { return dcgp::launch_count(); }
 
 int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH, int* OW, int* P, int* L) {
   if (H < f || W < f || f < 1 || s < 1 || C < 1) { set_error("bad view geometry"); return DCGP_ERR_ARG; }
@@ -298,27 +309,36 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
   const int M = d->M, R = d->R, L = p.L;
   cudaMemsetAsync(info, 0, sizeof(int), st);
   DCGP_TRY(rbf_sym_f64(Z, M, L, d->variance, d->lengthscale, d->jitter, w.Kuu, st));   // layers.py:18-21 / DS/layers.py:184
-  DCGP_TRY(build_operands(w, d->white, q_mu, q_sqrt, info, st));
-  if (algo == DCGP_ALGO_TC) {
-    DCGP_TRY(tc_pack_operands(p.tc, w.Linv, w.Mq, w.Wr, w.beta, M, p.Mp, R, st));
-    DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
-  } else {
-    DCGP_TRY(launch_pack_w(w.Linv, w.Mq, w.Wr, M, p.Mp, R, p.W, st));
-    DCGP_TRY(launch_pack_wmean(w.beta, M, p.Mp, R, p.RP, p.Wmean, st));
-  }
   DCGP_TRY(launch_pack_z(Z, (long long)M * L, 1.0 / d->lengthscale, p.zs, st));
-  // KL.  ConvLayer: prior covariance is Kuu at the *initial* Z with the live kernel hyper-parameters
-  // (layers.py:149-150); SVGP_Layer: the current Ku (DS/layers.py:242-256).
+  // KL prior.  ConvLayer: Kuu at the *initial* Z with the live kernel hyper-parameters (layers.py:149-150, SURVEY
+  // App. C3); SVGP_Layer: the current Ku (DS/layers.py:242-256).
   const bool own_prior = (d->kind == DCGP_LAYER_CONV) && Z_prior && Z_prior != Z && !d->white;
+  GInfo gi;
+  DCGP_TRY(factor_and_G(w, d->white, q_mu, info, &gi, st));
+  const double* Lp = w.Kuu;        // Cholesky factor of the prior covariance and its inverse
+  const double* Lpinv = w.Linv;
+  double* Kp = w.Wr;               // scratch that is free at this point on both paths
   if (own_prior) {
-    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, w.Kinv, st));
-    DCGP_TRY(potrf_f64(w.Kinv, M, M, w.invDp, info, st));
-    DCGP_TRY(trtri_f64(w.Kinv, M, M, w.invDp, w.Lpinv, w.trws, st));
-    DCGP_TRY(kl_terms(w, 0, w.Kinv, M, w.Lpinv, w.Mq, q_mu, q_sqrt, kl, st));
-  } else {
-    DCGP_TRY(kl_terms(w, d->white, w.Kuu, M, w.Linv, w.Mq, q_mu, q_sqrt, kl, st));
+    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, Kp, st));
+    DCGP_TRY(potrf_f64(Kp, M, M, w.invDp, info, st));
+    DCGP_TRY(trtri_f64(Kp, M, M, w.invDp, w.Lpinv, w.trws, st));
+    Lp = Kp;
+    Lpinv = w.Lpinv;
   }
-  return DCGP_OK;
+  if (algo == DCGP_ALGO_TC) {
+    DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
+                               w.beta, w.sc + 1, st));
+    DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+    return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
+  }
+  if (own_prior) {   // the fp64 path needs w.Wr for W_r first: move the prior factor out of the way
+    cudaMemcpyAsync(w.Kinv == gi.G ? w.tmpK : w.Kinv, Kp, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToDevice, st);
+    Lp = (w.Kinv == gi.G) ? w.tmpK : w.Kinv;
+  }
+  DCGP_TRY(wr_f64(w, d->white, gi, q_sqrt, st));
+  DCGP_TRY(launch_pack_w(w.Linv, w.Mq, w.Wr, M, p.Mp, R, p.W, st));
+  DCGP_TRY(launch_pack_wmean(w.beta, M, p.Mp, R, p.RP, p.Wmean, st));
+  return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st);
 }
 
 // ---------------------------------------------------------------------------------------------- layer apply

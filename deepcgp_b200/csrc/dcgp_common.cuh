@@ -9,7 +9,8 @@
 namespace dcgp {
 
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what, int n_launched = 1);   // also counts kernel launches (dcgp_launch_count)
+long long launch_count();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

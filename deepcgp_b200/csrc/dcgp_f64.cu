@@ -17,7 +17,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
-int check_launch(const char* what) {
+static long long g_launches = 0;
+long long launch_count() { return g_launches; }
+int check_launch(const char* what, int n_launched) {
+  g_launches += n_launched;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -142,38 +145,75 @@ int rbf_sym_f64(const double* Z, int M, int L, double variance, double lengthsca
 // ------------------------------------------------------------------------------------------ Cholesky
 // Diagonal block: factor an nb<=64 block held in shared memory and also form its inverse (used for the panel
 // solve and as the seed of the triangular inverse).  Padding rows/cols behave as identity.
+// Blocked inside the CTA (16-wide panels: warp-level factor, row-parallel panel solve, rank-16 trailing update), then
+// the inverse by recursive doubling on 16 -> 32 -> 64 blocks: a dozen block barriers instead of ~200.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int lda, int j0, int nb,
                                                          double* __restrict__ invD, int* __restrict__ info) {
   extern __shared__ double dyn_smem[];
   double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
   double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
-  const int tid = threadIdx.x;
+  double (*tm)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + 2 * NB * (NB + 1));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, j = e % NB;
+    const int i = e >> 6, j = e & 63;
     double v = (i == j) ? 1.0 : 0.0;
     if (i < nb && j < nb) v = (j <= i) ? A[(long long)(j0 + i) * lda + j0 + j] : 0.0;
     s[i][j] = v;
     x[i][j] = 0.0;
   }
   __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    if (tid == 0) {
-      const double p = s[k][k];
-      if (!(p > 0.0)) {
-        atomicCAS(info, 0, j0 + k + 1);
-        s[k][k] = nan("");
-      } else {
-        s[k][k] = sqrt(p);
+  for (int k0 = 0; k0 < NB; k0 += 16) {
+    if (warp == 0) {   // 16x16 diagonal block, one warp
+      for (int k = 0; k < 16; ++k) {
+        if (lane == 0) {
+          const double p = s[k0 + k][k0 + k];
+          if (!(p > 0.0)) {
+            atomicCAS(info, 0, j0 + k0 + k + 1);
+            s[k0 + k][k0 + k] = nan("");
+          } else {
+            s[k0 + k][k0 + k] = sqrt(p);
+          }
+        }
+        __syncwarp();
+        const double dkk = s[k0 + k][k0 + k];
+        if (lane > k && lane < 16) s[k0 + lane][k0 + k] /= dkk;
+        __syncwarp();
+#pragma unroll
+        for (int e = lane; e < 256; e += 32) {
+          const int i = e >> 4, j = e & 15;
+          if (j > k && j <= i) s[k0 + i][k0 + j] -= s[k0 + i][k0 + k] * s[k0 + j][k0 + k];
+        }
+        __syncwarp();
       }
     }
     __syncthreads();
-    const double dkk = s[k][k];
-    for (int i = k + 1 + tid; i < nb; i += 256) s[i][k] /= dkk;
+    // panel below the diagonal block: row i solves x * Lkk^T = a  (forward substitution along the 16 columns)
+    if (tid < NB - k0 - 16) {
+      const int i = k0 + 16 + tid;
+      double r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = s[i][k0 + j];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double v = r[j];
+#pragma unroll
+        for (int l = 0; l < j; ++l) v = fma(-r[l], s[k0 + j][k0 + l], v);
+        r[j] = v / s[k0 + j][k0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s[i][k0 + j] = r[j];
+    }
     __syncthreads();
-    const int n = nb - k - 1;
+    // rank-16 update of the trailing lower triangle
+    const int n = NB - k0 - 16;
     for (int e = tid; e < n * n; e += 256) {
-      const int i = k + 1 + e / n, j = k + 1 + e % n;
-      if (j <= i) s[i][j] -= s[i][k] * s[j][k];
+      const int i = k0 + 16 + e / n, j = k0 + 16 + e % n;
+      if (j <= i) {
+        double v = s[i][j];
+#pragma unroll
+        for (int l = 0; l < 16; ++l) v = fma(-s[i][k0 + l], s[j][k0 + l], v);
+        s[i][j] = v;
+      }
     }
     __syncthreads();
   }
@@ -181,18 +221,38 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
     const int i = e / nb, j = e % nb;
     A[(long long)(j0 + i) * lda + j0 + j] = (j <= i) ? s[i][j] : 0.0;
   }
-  // inverse by forward substitution, one column per thread
+  // ---- inverse: 16x16 diagonal blocks by forward substitution (one column per thread) ...
   if (tid < NB) {
-    const int c = tid;
+    const int b0 = (tid >> 4) << 4, c = tid;
     x[c][c] = 1.0 / s[c][c];
-    for (int i = c + 1; i < NB; ++i) {
+    for (int i = c + 1; i < b0 + 16; ++i) {
       double acc = 0.0;
       for (int k = c; k < i; ++k) acc = fma(s[i][k], x[k][c], acc);
       x[i][c] = -acc / s[i][i];
     }
   }
   __syncthreads();
-  for (int e = tid; e < NB * NB; e += 256) invD[e] = x[e / NB][e % NB];
+  // ... then inv([[A,0],[C,B]]) = [[A^-1,0],[-B^-1 C A^-1, B^-1]] for block sizes 16 and 32
+  for (int sz = 16; sz < NB; sz *= 2) {
+    const int npairs = NB / (2 * sz);
+    for (int e = tid; e < npairs * sz * sz; e += 256) {   // T = C * A^-1
+      const int pr = e / (sz * sz), r = (e / sz) % sz, c = e % sz;
+      const int a0 = pr * 2 * sz, b0 = a0 + sz;
+      double acc = 0.0;
+      for (int k = c; k < sz; ++k) acc = fma(s[b0 + r][a0 + k], x[a0 + k][a0 + c], acc);
+      tm[b0 + r][a0 + c] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < npairs * sz * sz; e += 256) {   // X_ba = -B^-1 * T
+      const int pr = e / (sz * sz), r = (e / sz) % sz, c = e % sz;
+      const int a0 = pr * 2 * sz, b0 = a0 + sz;
+      double acc = 0.0;
+      for (int k = 0; k <= r; ++k) acc = fma(x[b0 + r][b0 + k], tm[b0 + k][a0 + c], acc);
+      x[b0 + r][a0 + c] = -acc;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < NB * NB; e += 256) invD[e] = x[e >> 6][e & 63];
 }
 
 // Panel solve: A[i, j0:j0+nb] <- A[i, j0:j0+nb] * inv(Ljj)^T for rows i >= j0+nb, 64 rows per CTA.
@@ -226,7 +286,7 @@ __global__ void zero_upper_kernel(double* __restrict__ A, int lda, int M) {
 
 size_t potrf_ws_bytes(int M) { return (size_t)ceil_div(M, NB) * NB * NB * sizeof(double); }
 
-constexpr int kDiagSmem = 2 * NB * (NB + 1) * sizeof(double);
+constexpr int kDiagSmem = 3 * NB * (NB + 1) * sizeof(double);
 
 int potrf_f64(double* A, int lda, int M, double* invD, int* info, cudaStream_t st) {
   static bool attr_set = false;
@@ -254,7 +314,7 @@ int potrf_f64(double* A, int lda, int M, double* invD, int* info, cudaStream_t s
       trsm_panel_kernel<<<ceil_div(rows_below, NB), 256, kDiagSmem, st>>>(A, lda, M, j0, nb, invD + (size_t)jb * NB * NB);
   }
   zero_upper_kernel<<<dim3(ceil_div(M, 256), M), 256, 0, st>>>(A, lda, M);
-  return check_launch("potrf_f64");
+  return check_launch("potrf_f64", 2 * nblk);   // nblk diag + (nblk-1) panel solves + zero_upper
 }
 
 // ------------------------------------------------------------------------------------------ L^-1
@@ -310,7 +370,7 @@ int trtri_f64(const double* L, int lda, int M, const double* invD, double* Linv,
     rc = gemm_f64(g2, st);
     if (rc) return rc;
   }
-  return check_launch("trtri_f64");
+  return check_launch("trtri_f64", 1);
 }
 
 // ------------------------------------------------------------------------------------------ reductions
@@ -328,11 +388,12 @@ __device__ __forceinline__ double block_sum_1024(double v) {
   return v;
 }
 
+// Multi-CTA: every CTA reduces a slice and adds its partial with one double atomicAdd (out must be zeroed first).
 __global__ void __launch_bounds__(1024) sumsq_f64_kernel(const double* __restrict__ x, long long rows, int cols, int ld,
                                                          int lower_period, double* __restrict__ out) {
   double acc = 0.0;
   const long long n = rows * cols;
-  for (long long e = threadIdx.x; e < n; e += 1024) {
+  for (long long e = blockIdx.x * 1024LL + threadIdx.x; e < n; e += 1024LL * gridDim.x) {
     const long long r = e / cols;
     const int c = (int)(e % cols);
     if (lower_period > 0 && c > (int)(r % lower_period)) continue;
@@ -340,11 +401,16 @@ __global__ void __launch_bounds__(1024) sumsq_f64_kernel(const double* __restric
     acc = fma(v, v, acc);
   }
   acc = block_sum_1024(acc);
-  if (threadIdx.x == 0) *out = acc;
+  if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 
 int sumsq_f64(const double* x, long long rows, int cols, int ld, int lower_period, double* out, cudaStream_t st) {
-  sumsq_f64_kernel<<<1, 1024, 0, st>>>(x, rows, cols, ld, lower_period, out);
+  cudaMemsetAsync(out, 0, sizeof(double), st);
+  const long long n = rows * cols;
+  int blocks = (int)((n + 8191) / 8192);
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148) blocks = 148;
+  sumsq_f64_kernel<<<blocks, 1024, 0, st>>>(x, rows, cols, ld, lower_period, out);
   return check_launch("sumsq_f64");
 }
 

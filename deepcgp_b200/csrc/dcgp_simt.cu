@@ -504,7 +504,7 @@ int launch_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, 
   const int SN = S * N;
   varexp_kernel<<<ceil_div(SN, 128), 128, 0, st>>>(Fmu, Fvar, Y, SN, N, K, log(1.0 - epsilon), log(epsilon / (K - 1.0)), varexp);
   sum_f64_kernel<<<1, 1024, 0, st>>>(varexp, SN, sum);
-  return check_launch("varexp");
+  return check_launch("varexp", 2);
 }
 
 __global__ void elbo_kernel(const double* sum_varexp, int S, double scale, const double* kls, int n_layers, double* elbo) {

@@ -129,23 +129,57 @@ struct CondCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-struct CondParams {
+constexpr int MODE_COND = 0;   // conditional GEMM: per-row-block sums of squares + mean rows
+constexpr int MODE_GEMM = 1;   // plain batched C = A * B^T: store fp32 and/or accumulate the sum of squares of C
+
+struct TcParams {
+  int n_items;
+  int nkb;        // K-dimension blocks of 64
+  // ---- MODE_COND
   int T;          // valid patch-columns
-  int n_ttiles;   // ceil(T / 128)
   int Mp;         // padded inducing points (multiple of 64)
   int R;
   int njt;        // Mp / BN  (j-tiles per row block)
-  int n_items;    // n_ttiles * (R + 2)
   const float* wscal;  // device: [0]=W scale, [1]=1/W scale, [2]=Wmean scale, [3]=1/Wmean scale
   const float* kscal;  // device: [0]=K scale, [1]=1/K scale
   float* acc;     // [T, R+1]
   float* mean;    // [T, R]
+  // ---- MODE_GEMM: C[b][i, j] = sum_k A[b*a_batch_rows + i, k] * B[b*b_batch_rows + j, k]
+  int m_tiles, n_tiles;
+  int a_batch_rows, b_batch_rows;
+  int m_valid, n_valid;
+  const float* a_scal;   // device {scale, 1/scale} of the A planes
+  const float* b_scal;   // device {scale, 1/scale} of the B planes
+  float* C;              // may be null
+  long long c_batch_stride;
+  int ldc;
+  double* sq_out;        // may be null: += sum of squares of all valid C entries
 };
 
-template <int BN>
+template <int MODE, int BN>
+__device__ __forceinline__ int tiles_in_item(const TcParams& p, int item) {
+  if (MODE == MODE_COND) return (item % (p.R + 2) == p.R + 1) ? 1 : p.njt;
+  return 1;
+}
+template <int MODE, int BN>
+__device__ __forceinline__ void tile_rows(const TcParams& p, int item, int jt, int& a_row, int& b_row) {
+  if (MODE == MODE_COND) {
+    const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
+    a_row = tt * kBM;
+    b_row = blk * p.Mp + jt * BN;
+  } else {
+    const int per = p.m_tiles * p.n_tiles;
+    const int b = item / per, rem = item - b * per;
+    const int it = rem / p.n_tiles, jn = rem - it * p.n_tiles;
+    a_row = b * p.a_batch_rows + it * kBM;
+    b_row = b * p.b_batch_rows + jn * BN;
+  }
+}
+
+template <int MODE, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-cond_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, CondParams p) {
+tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
   using Cfg = CondCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-B alignment
@@ -156,7 +190,7 @@ cond_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = p.Mp / kBK;
+  const int nkb = p.nkb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
@@ -176,16 +210,16 @@ cond_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
-        const int njt = (blk == p.R + 1) ? 1 : p.njt;
+        const int njt = tiles_in_item<MODE, BN>(p, item);
         for (int jt = 0; jt < njt; ++jt) {
-          const int brow = blk * p.Mp + jt * BN;
+          int arow, brow;
+          tile_rows<MODE, BN>(p, item, jt, arow, brow);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(st, &tmA_hi, &full_bar[stage], kb * kBK, tt * kBM);
-            tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, tt * kBM);
+            tma_load_2d(st, &tmA_hi, &full_bar[stage], kb * kBK, arow);
+            tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, arow);
             tma_load_2d(st + 2 * Cfg::kStageA, &tmB_hi, &full_bar[stage], kb * kBK, brow);
             tma_load_2d(st + 2 * Cfg::kStageA + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb * kBK, brow);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
@@ -200,8 +234,7 @@ cond_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int stage = 0; uint32_t phase = 0;
       uint32_t tile = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
-        const int njt = (blk == p.R + 1) ? 1 : p.njt;
+        const int njt = tiles_in_item<MODE, BN>(p, item);
         for (int jt = 0; jt < njt; ++jt, ++tile) {
           const uint32_t buf = tile & 1, use = tile >> 1;
           mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
@@ -235,55 +268,103 @@ cond_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ------------------------------------------------------------------ epilogue: 4 warps <-> 4 TMEM lane quarters
     const int q = warp & 3;                                  // warps 2,3,4,5 -> quarters 2,3,0,1
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const float inv_w = p.wscal[1], inv_wm = p.wscal[3], inv_k = p.kscal[1];
-    const float sq_scale = (inv_w * inv_k) * (inv_w * inv_k);
-    const float mean_scale = inv_wm * inv_k;
     uint32_t tile = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
-      const bool is_mean = (blk == p.R + 1);
-      const int njt = is_mean ? 1 : p.njt;
-      const int t = tt * kBM + q * 32 + lane;
-      float ssq = 0.f;
-      for (int jt = 0; jt < njt; ++jt, ++tile) {
+    if (MODE == MODE_COND) {
+      const float inv_w = p.wscal[1], inv_wm = p.wscal[3], inv_k = p.kscal[1];
+      const float sq_scale = (inv_w * inv_k) * (inv_w * inv_k);
+      const float mean_scale = inv_wm * inv_k;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
+        const bool is_mean = (blk == p.R + 1);
+        const int njt = is_mean ? 1 : p.njt;
+        const int t = tt * kBM + q * 32 + lane;
+        float ssq = 0.f;
+        for (int jt = 0; jt < njt; ++jt, ++tile) {
+          const uint32_t buf = tile & 1, use = tile >> 1;
+          mbar_wait(&tmem_full[buf], use & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + lane_base + buf * BN;
+          if (is_mean) {
+            float v[32];
+            tmem_ld_32x32(taddr, v);
+            if (t < p.T) {
+#pragma unroll
+              for (int r = 0; r < 32; ++r)
+                if (r < p.R) p.mean[(long long)t * p.R + r] = v[r] * mean_scale;
+            }
+            if (p.R > 32) {
+              tmem_ld_32x32(taddr + 32, v);
+              if (t < p.T) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                  if (32 + r < p.R) p.mean[(long long)t * p.R + 32 + r] = v[r] * mean_scale;
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+              float v[32];
+              tmem_ld_32x32(taddr + c, v);
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
+                s2 = fmaf(v[i + 2], v[i + 2], s2); s3 = fmaf(v[i + 3], v[i + 3], s3);
+              }
+              ssq += (s0 + s1) + (s2 + s3);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        if (!is_mean && t < p.T) p.acc[(long long)t * (p.R + 1) + blk] = ssq * sq_scale;
+      }
+    } else {
+      const float inv = p.a_scal[1] * p.b_scal[1];
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
+        const int per = p.m_tiles * p.n_tiles;
+        const int b = item / per, rem = item - b * per;
+        const int it = rem / p.n_tiles, jn = rem - it * p.n_tiles;
+        const int row = it * kBM + q * 32 + lane;
         const uint32_t buf = tile & 1, use = tile >> 1;
         mbar_wait(&tmem_full[buf], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + buf * BN;
-        if (is_mean) {
-          float v[32];
-          tmem_ld_32x32(taddr, v);
-          if (t < p.T) {
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (r < p.R) p.mean[(long long)t * p.R + r] = v[r] * mean_scale;
-          }
-          if (p.R > 32) {
-            tmem_ld_32x32(taddr + 32, v);
-            if (t < p.T) {
-#pragma unroll
-              for (int r = 0; r < 32; ++r)
-                if (32 + r < p.R) p.mean[(long long)t * p.R + 32 + r] = v[r] * mean_scale;
-            }
-          }
-        } else {
+        float ssq = 0.f;
+        float* crow = p.C ? p.C + (long long)b * p.c_batch_stride + (long long)row * p.ldc : nullptr;
 #pragma unroll 1
-          for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            tmem_ld_32x32(taddr + c, v);
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          tmem_ld_32x32(taddr + c, v);
+          const int col0 = jn * BN + c;
+          if (row < p.m_valid && col0 < p.n_valid) {
+            if (col0 + 32 <= p.n_valid) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              s0 = fmaf(v[i], v[i], s0); s1 = fmaf(v[i + 1], v[i + 1], s1);
-              s2 = fmaf(v[i + 2], v[i + 2], s2); s3 = fmaf(v[i + 3], v[i + 3], s3);
+              for (int i = 0; i < 32; ++i) { v[i] *= inv; ssq = fmaf(v[i], v[i], ssq); }
+              if (crow) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4)
+                  *reinterpret_cast<float4*>(crow + col0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.n_valid) {
+                  const float x = v[i] * inv;
+                  ssq = fmaf(x, x, ssq);
+                  if (crow) crow[col0 + i] = x;
+                }
             }
-            ssq += (s0 + s1) + (s2 + s3);
           }
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[buf]);
+        if (p.sq_out) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
+          if (lane == 0) atomicAdd(p.sq_out, (double)ssq);
+        }
       }
-      if (!is_mean && t < p.T) p.acc[(long long)t * (p.R + 1) + blk] = ssq * sq_scale;
     }
   }
   tc_fence_before();
@@ -338,28 +419,59 @@ constexpr int kWPadRows = 256;   // zero rows after the mean block so a BN-row b
 
 static size_t w_rows(int Mp, int R) { return (size_t)(R + 1) * Mp + kWPadRows; }
 
+template <int MODE, int BN>
+static int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl,
+                     const TcParams& p, cudaStream_t st) {
+  using Cfg = CondCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("tc_kernel smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
+    attr = true;
+  }
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  if (grid <= 0) return DCGP_OK;
+  tc_kernel<MODE, BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmAh, tmAl, tmBh, tmBl, p);
+  return check_launch("tc_kernel");
+}
+
 template <int BN>
 static int launch_cond_tc(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st) {
-  using Cfg = CondCfg<BN>;
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
   int rc;
   if ((rc = make_tmap_f16(&tmAh, w.Kh, w.Tpad, Mp, kBM))) return rc;
   if ((rc = make_tmap_f16(&tmAl, w.Kl, w.Tpad, Mp, kBM))) return rc;
   if ((rc = make_tmap_f16(&tmBh, prep.Wh, w_rows(Mp, R), Mp, BN))) return rc;
   if ((rc = make_tmap_f16(&tmBl, prep.Wl, w_rows(Mp, R), Mp, BN))) return rc;
-  CondParams p;
-  p.T = T; p.n_ttiles = ceil_div(T, kBM); p.Mp = Mp; p.R = R; p.njt = Mp / BN;
-  p.n_items = p.n_ttiles * (R + 2);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.Mp = Mp; p.R = R; p.njt = Mp / BN; p.nkb = Mp / kBK;
+  p.n_items = ceil_div(T, kBM) * (R + 2);
   p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(cond_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) { set_error("cond_tc smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
-    attr = true;
-  }
-  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
-  cond_tc_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmAh, tmAl, tmBh, tmBl, p);
-  return check_launch("cond_tc");
+  return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, p, st);
+}
+
+// Batched C[b] = A[b] * B[b]^T on split-fp16 planes (both K-major, row-stacked batches); rows/K padded by the caller.
+int tc_gemm(const TcGemm& g, cudaStream_t st) {
+  const int BN = (g.n_pad % 256 == 0) ? 256 : (g.n_pad % 128 == 0 ? 128 : 64);
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  int rc;
+  if ((rc = make_tmap_f16(&tmAh, g.Ah, g.a_rows_total, g.k_pad, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmAl, g.Al, g.a_rows_total, g.k_pad, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmBh, g.Bh, g.b_rows_total, g.k_pad, BN))) return rc;
+  if ((rc = make_tmap_f16(&tmBl, g.Bl, g.b_rows_total, g.k_pad, BN))) return rc;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.nkb = g.k_pad / kBK;
+  p.m_tiles = g.m_pad / kBM; p.n_tiles = g.n_pad / BN;
+  p.n_items = g.batch * p.m_tiles * p.n_tiles;
+  p.a_batch_rows = g.a_batch_rows; p.b_batch_rows = g.b_batch_rows;
+  p.m_valid = g.m; p.n_valid = g.n;
+  p.a_scal = g.a_scal; p.b_scal = g.b_scal;
+  p.C = g.C; p.c_batch_stride = g.c_batch_stride; p.ldc = g.ldc; p.sq_out = g.sq_out;
+  if (BN == 256) return launch_tc<MODE_GEMM, 256>(tmAh, tmAl, tmBh, tmBl, p, st);
+  if (BN == 128) return launch_tc<MODE_GEMM, 128>(tmAh, tmAl, tmBh, tmBl, p, st);
+  return launch_tc<MODE_GEMM, 64>(tmAh, tmAl, tmBh, tmBl, p, st);
 }
 
 int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st) {
@@ -375,46 +487,53 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn(x - __half2float(hi));
 }
 
-// max |x| over a float64 array -> power-of-two scale that maps it to [2^13, 2^14)  (fp16 max is 65504).
-__global__ void __launch_bounds__(1024) scale_from_max_f64_kernel(const double* __restrict__ a, long long na, int lda, int cols,
-                                                                  const double* __restrict__ b, long long nb,
-                                                                  float* __restrict__ scal2) {
-  __shared__ double sh[32];
-  double m = 0.0;
-  for (long long e = threadIdx.x; e < na; e += 1024) {
-    const long long r = e / cols;
-    const int c = (int)(e % cols);
-    m = fmax(m, fabs(a[r * lda + c]));
-  }
-  for (long long e = threadIdx.x; e < nb; e += 1024) m = fmax(m, fabs(b[e]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 32; ++i) m = fmax(m, sh[i]);
-    int e = 0;
-    if (m > 0.0 && isfinite(m)) { frexp(m, &e); }   // m = f * 2^e, f in [0.5, 1)
-    const float s = ldexpf(1.f, 14 - e);
-    scal2[0] = s;
-    scal2[1] = 1.f / s;
-  }
+// ---- power-of-two scaling: planes hold x * s with s = 2^(14 - e), max|x| = f * 2^e (f in [0.5,1)), so that the largest
+// entry lands in [2^13, 2^14) (fp16 max is 65504) and small entries keep their 22 bits.
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {   // valid for v >= 0 (IEEE order == int order)
+  atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
 }
-__global__ void __launch_bounds__(1024) scale_from_max_f32_kernel(const float* __restrict__ a, long long n, float* __restrict__ scal2) {
-  __shared__ float sh[32];
-  float m = 0.f;
-  for (long long e = threadIdx.x; e < n; e += 1024) m = fmaxf(m, fabsf(a[e]));
+__device__ __forceinline__ float block_max_256(float m) {
+  __shared__ float sh[8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 32; ++i) m = fmaxf(m, sh[i]);
+  if (threadIdx.x < 8) m = sh[threadIdx.x]; else m = 0.f;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  return m;
+}
+// mx[slot] = max(mx[slot], max |a[r*ld + c]|) over rows x cols (mx zeroed beforehand); lower_period > 0 masks c > r % period
+__global__ void __launch_bounds__(256) maxabs_f64_kernel(const double* __restrict__ a, long long rows, int cols, int ld,
+                                                         int lower_period, float* __restrict__ mx) {
+  float m = 0.f;
+  const long long n = rows * cols;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += 256LL * gridDim.x) {
+    const long long r = e / cols;
+    const int c = (int)(e % cols);
+    if (lower_period > 0 && c > (int)(r % lower_period)) continue;
+    m = fmaxf(m, (float)fabs(a[r * ld + c]));
+  }
+  m = block_max_256(m);
+  if (threadIdx.x == 0) atomic_max_nonneg(mx, m);
+}
+__global__ void __launch_bounds__(256) maxabs_f32_kernel(const float* __restrict__ a, long long n, float* __restrict__ mx) {
+  float m = 0.f;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += 256LL * gridDim.x) m = fmaxf(m, fabsf(a[e]));
+  m = block_max_256(m);
+  if (threadIdx.x == 0) atomic_max_nonneg(mx, m);
+}
+__global__ void scales_from_max_kernel(const float* __restrict__ mx, int first, int count, float* __restrict__ scal) {
+  const int i = first + threadIdx.x;
+  if (threadIdx.x < count) {
+    const float m = mx[i];
     int e = 0;
-    if (m > 0.f && isfinite(m)) { frexpf(m, &e); }
+    if (m > 0.f && isfinite(m)) frexpf(m, &e);
     const float s = ldexpf(1.f, 14 - e);
-    scal2[0] = s;
-    scal2[1] = 1.f / s;
+    scal[2 * i] = s;
+    scal[2 * i + 1] = 1.f / s;
   }
 }
 __global__ void set_scale_kernel(float bound, float* __restrict__ scal2) {
@@ -424,11 +543,56 @@ __global__ void set_scale_kernel(float bound, float* __restrict__ scal2) {
   scal2[0] = s;
   scal2[1] = 1.f / s;
 }
+static int grid_for(long long n, int per_block) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > 148 * 4) b = 148 * 4;
+  return (int)b;
+}
+static int maxabs_f64(const double* a, long long rows, int cols, int ld, int lower_period, float* mx, cudaStream_t st) {
+  maxabs_f64_kernel<<<grid_for(rows * cols, 2048), 256, 0, st>>>(a, rows, cols, ld, lower_period, mx);
+  return check_launch("maxabs_f64");
+}
+static int maxabs_f32(const float* a, long long n, float* mx, cudaStream_t st) {
+  maxabs_f32_kernel<<<grid_for(n, 4096), 256, 0, st>>>(a, n, mx);
+  return check_launch("maxabs_f32");
+}
+
+// Generic fp64 -> split-fp16 planes: dst[b*rows_pad + i, j] = s * src_b(i, j), where src_b(i,j) = src[b*bstride + i*ld + j]
+// (or its transpose src[b*bstride + j*ld + i]); `lower` zeroes STORED entries above the diagonal; zero padding elsewhere.
+__global__ void __launch_bounds__(256) pack_planes_f64_kernel(const double* __restrict__ src, int ld, long long bstride, int rows,
+                                                              int cols, int transpose, int lower, int batch, int rows_pad,
+                                                              int cols_pad, const float* __restrict__ scal2,
+                                                              __half* __restrict__ Ph, __half* __restrict__ Pl) {
+  const double s = (double)scal2[0];
+  const long long total = (long long)batch * rows_pad * cols_pad;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    const int j = (int)(e % cols_pad);
+    const long long q = e / cols_pad;
+    const int i = (int)(q % rows_pad), b = (int)(q / rows_pad);
+    double v = 0.0;
+    if (i < rows && j < cols) {
+      const int sr = transpose ? j : i, sc = transpose ? i : j;
+      if (!lower || sc <= sr) v = s * src[b * bstride + (long long)sr * ld + sc];
+    }
+    const __half hi = __float2half_rn((float)v);
+    Ph[e] = hi;
+    Pl[e] = __float2half_rn((float)(v - (double)__half2float(hi)));
+  }
+}
+static int pack_planes_f64(const double* src, int ld, long long bstride, int rows, int cols, int transpose, int lower, int batch,
+                           int rows_pad, int cols_pad, const float* scal2, void* Ph, void* Pl, cudaStream_t st) {
+  pack_planes_f64_kernel<<<grid_for((long long)batch * rows_pad * cols_pad, 2048), 256, 0, st>>>(
+      src, ld, bstride, rows, cols, transpose, lower, batch, rows_pad, cols_pad, scal2, (__half*)Ph, (__half*)Pl);
+  return check_launch("pack_planes_f64");
+}
 
 // W planes: rows [0, (R+1)*Mp) = blocks (block 0 = Linv, block r = Wr[r-1]), then the mean rows (beta^T), then zero padding.
-__global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, const double* __restrict__ Wr,
-                                  const double* __restrict__ beta, int M, int Mp, int R, long long rows_total,
-                                  const float* __restrict__ scal, __half* __restrict__ Wh, __half* __restrict__ Wl) {
+// Wr comes either as float64 [R, M, M] (Wr64) or as float32 [R*Mp, Mp] (Wr32, the tensor-core product).
+__global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, const double* __restrict__ Wr64,
+                                  const float* __restrict__ Wr32, const double* __restrict__ beta, int M, int Mp, int R,
+                                  long long rows_total, const float* __restrict__ scal, __half* __restrict__ Wh,
+                                  __half* __restrict__ Wl) {
   const double sw = (double)scal[0], swm = (double)scal[2];
   const long long total = rows_total * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -438,18 +602,20 @@ __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, cons
     if (j < M) {
       if (row < (long long)(R + 1) * Mp) {
         const int blk = (int)(row / Mp), i = (int)(row % Mp);
-        if (i < M) v = sw * ((blk == 0) ? Linv[(long long)i * ldl + j] : Wr[((long long)(blk - 1) * M + i) * M + j]);
+        if (i < M) {
+          if (blk == 0) v = sw * Linv[(long long)i * ldl + j];
+          else if (Wr64) v = sw * Wr64[((long long)(blk - 1) * M + i) * M + j];
+          else v = sw * (double)Wr32[((long long)(blk - 1) * Mp + i) * Mp + j];
+        }
       } else {
         const int r = (int)(row - (long long)(R + 1) * Mp);
         if (r < R) v = swm * beta[(long long)j * R + r];
       }
     }
-    const float x = (float)v;
-    __half hi = __float2half_rn(x);
+    const __half hi = __float2half_rn((float)v);
     // the low part is taken from the float64 value so that hi + lo carries 22 bits of the original
-    __half lo = __float2half_rn((float)(v - (double)__half2float(hi)));
     Wh[e] = hi;
-    Wl[e] = lo;
+    Wl[e] = __float2half_rn((float)(v - (double)__half2float(hi)));
   }
 }
 
@@ -489,19 +655,79 @@ void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   t.Zh = c.take((size_t)Mp * t.Lp * 2);
   t.Zl = c.take((size_t)Mp * t.Lp * 2);
   t.zz = (float*)c.take((size_t)Mp * 4);
-  t.scal = (float*)c.take(8 * 4);
+  t.scal = (float*)c.take(16 * 4);
+  t.mx = (float*)c.take(8 * 4);
+  t.QTh = c.take((size_t)R * Mp * Mp * 2);
+  t.QTl = c.take((size_t)R * Mp * Mp * 2);
+  t.Gh = c.take((size_t)Mp * Mp * 2);
+  t.Gl = c.take((size_t)Mp * Mp * 2);
+  t.Lph = c.take((size_t)Mp * Mp * 2);
+  t.Lpl = c.take((size_t)Mp * Mp * 2);
+  t.Wr32 = (float*)c.take((size_t)R * Mp * Mp * 4);
   t.Wmh = t.Wml = nullptr;
   t.bytes = align_up(c.off, 1024);
 }
 
+// scal slots: 0 = W blocks, 1 = mean rows, 2 = q_sqrt^T planes, 3 = G planes, 4 = Lp^-1 planes  ({scale, 1/scale} each)
 int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double* Wr, const double* beta, int M, int Mp, int R,
                      cudaStream_t st) {
-  // scale of the variance blocks: max over Linv (M x M, ld ldl) and Wr (R*M*M contiguous); of the mean rows: max over beta
-  scale_from_max_f64_kernel<<<1, 1024, 0, st>>>(Linv, (long long)M * M, ldl, M, Wr, (long long)R * M * M, t.scal + 0);
-  scale_from_max_f64_kernel<<<1, 1024, 0, st>>>(beta, (long long)M * R, R, R, nullptr, 0, t.scal + 2);
-  pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, Wr, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal, (__half*)t.Wh,
-                                                   (__half*)t.Wl);
-  return check_launch("tc_pack_operands");
+  cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
+  int rc;
+  if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 0, st))) return rc;
+  if ((rc = maxabs_f64(Wr, (long long)R * M, M, M, 0, t.mx + 0, st))) return rc;
+  if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 1, st))) return rc;
+  scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
+  pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, Wr, nullptr, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
+                                                   (__half*)t.Wh, (__half*)t.Wl);
+  return check_launch("tc_pack_operands", 2);
+}
+
+// Tensor-core build of the R-batched M-only products (the O(R M^3) part of the step's minibatch-independent work):
+//   W_r = L_r^T G            (G = Kuu^-1 symmetric, or Lm^-1 when whitened)                -> fp32, then the W planes
+//   trace = sum_r |Lp^-1 L_r|_F^2   (GPflow gauss_kl / DS/layers.py:250)                  -> *trace_out (double)
+// Linv/G/Lpinv/beta are float64 (Cholesky-quality); only these products run split-fp16 on tcgen05.
+int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
+                      const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out, cudaStream_t st) {
+  const int M = t.M, Mp = t.Mp, R = t.R;
+  int rc;
+  cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
+  if ((rc = maxabs_f64(q_sqrt, (long long)R * M, M, M, M, t.mx + 2, st))) return rc;
+  if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc;
+  if (Lpinv && (rc = maxabs_f64(Lpinv, M, M, ldp, 0, t.mx + 4, st))) return rc;
+  scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 2, 3, t.scal);
+  check_launch("scales_from_max");
+  // QT[r*Mp + i, k] = L_r[k, i]  (transpose of the lower-triangular q_sqrt_r)
+  if ((rc = pack_planes_f64(q_sqrt, M, (long long)M * M, M, M, 1, 1, R, Mp, Mp, t.scal + 4, t.QTh, t.QTl, st))) return rc;
+  // B operand of W_r: B[j, k] = G[k, j]  (G symmetric when it is Kuu^-1; the transpose of Lm^-1 when whitened)
+  if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
+  TcGemm g;
+  memset(&g, 0, sizeof(g));
+  g.Ah = t.QTh; g.Al = t.QTl; g.a_rows_total = (long long)R * Mp; g.a_batch_rows = Mp;
+  g.Bh = t.Gh; g.Bl = t.Gl; g.b_rows_total = Mp; g.b_batch_rows = 0;
+  g.batch = R; g.m = M; g.n = M; g.m_pad = Mp; g.n_pad = Mp; g.k_pad = Mp;
+  g.a_scal = t.scal + 4; g.b_scal = t.scal + 6;
+  g.C = t.Wr32; g.c_batch_stride = (long long)Mp * Mp; g.ldc = Mp;
+  if ((rc = tc_gemm(g, st))) return rc;
+  if (Lpinv) {
+    if ((rc = pack_planes_f64(Lpinv, ldp, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 8, t.Lph, t.Lpl, st))) return rc;
+    cudaMemsetAsync(trace_out, 0, sizeof(double), st);
+    TcGemm h;
+    memset(&h, 0, sizeof(h));
+    h.Ah = t.Lph; h.Al = t.Lpl; h.a_rows_total = Mp; h.a_batch_rows = 0;
+    h.Bh = t.QTh; h.Bl = t.QTl; h.b_rows_total = (long long)R * Mp; h.b_batch_rows = Mp;
+    h.batch = R; h.m = M; h.n = M; h.m_pad = Mp; h.n_pad = Mp; h.k_pad = Mp;
+    h.a_scal = t.scal + 8; h.b_scal = t.scal + 4;
+    h.sq_out = trace_out;
+    if ((rc = tc_gemm(h, st))) return rc;
+  }
+  // W planes for the conditional GEMM: block 0 = Lm^-1 (float64), blocks 1..R = W_r (fp32 product), mean rows = beta^T
+  if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 0, st))) return rc;
+  if ((rc = maxabs_f32(t.Wr32, (long long)R * Mp * Mp, t.mx + 0, st))) return rc;
+  if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 1, st))) return rc;
+  scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
+  pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
+                                                   (__half*)t.Wh, (__half*)t.Wl);
+  return check_launch("tc_build_operands", 2);
 }
 
 int tc_pack_z(const TcPrep&, const double*, int, int, double, cudaStream_t) { return DCGP_OK; }  // used by the tensor-core Kuf kernel
@@ -520,9 +746,11 @@ void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf) {
 }
 
 int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStream_t st) {
-  scale_from_max_f32_kernel<<<1, 1024, 0, st>>>(Kt, (long long)T * Mp, w.kscal);
+  cudaMemsetAsync(w.kscal + 4, 0, sizeof(float), st);
+  maxabs_f32_kernel<<<grid_for((long long)T * Mp, 4096), 256, 0, st>>>(Kt, (long long)T * Mp, w.kscal + 4);
+  scales_from_max_kernel<<<1, 32, 0, st>>>(w.kscal + 4, 0, 1, w.kscal);
   split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(Kt, T, Mp, (long long)w.Tpad, w.kscal, (__half*)w.Kh, (__half*)w.Kl);
-  return check_launch("tc_split_rows");
+  return check_launch("tc_split_rows", 3);
 }
 
 void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, void* buf) {
@@ -549,6 +777,7 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
   if (d->kind == DCGP_LAYER_CONV) {
     const int T = n_rows * v.P;
     set_scale_kernel<<<1, 1, 0, st>>>(variance, a.kk.kscal);      // RBF values lie in (0, variance]
+    check_launch("set_scale");
     int rc = launch_kuf_simt_planes(X, v, n_rows, zs, M, variance, inv_ls, Mp, a.kk.kscal, a.kk.Kh, a.kk.Kl, (long long)a.kk.Tpad, st);
     if (rc) return rc;
     return tc_cond(prep, a.kk, T, Mp, R, acc, mean_t, st);

@@ -13,12 +13,19 @@ struct TcPrep {
   void *Wmh, *Wml;   // [64, Mp] fp16 (mean rows, zero padded)
   void *Zh, *Zl;     // [Mp, Lp] fp16 (Z / lengthscale)
   float* zz;         // [Mp] |z/ls|^2 (fp32, from fp64)
-  float* scal;       // [8] device scalars: 0: W scale, 1: 1/Wscale, 2: Wmean scale, 3: 1/Wmean scale
+  float* scal;       // [16] device {scale, 1/scale} pairs: W blocks, mean rows, q_sqrt^T, G, Lp^-1
+  float* mx;         // [8] running max |x| per slot
+  void *QTh, *QTl;   // [R*Mp, Mp] fp16: transposed q_sqrt planes (A operand of W_r = L_r^T G, B operand of Lp^-1 L_r)
+  void *Gh, *Gl;     // [Mp, Mp]
+  void *Lph, *Lpl;   // [Mp, Mp]
+  float* Wr32;       // [R*Mp, Mp] fp32 W_r (tensor-core product)
   size_t bytes;
 };
 void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf);
 int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double* Wr, const double* beta, int M, int Mp,
                      int R, cudaStream_t st);
+int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
+                      const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out, cudaStream_t st);
 int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st);
 
 struct TcCondWork {
@@ -31,6 +38,19 @@ struct TcCondWork {
 void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf);
 int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStream_t st);
 int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st);
+
+// Generic batched NT GEMM on split-fp16 planes: C[b][i,j] = sum_k A[b*a_batch_rows + i, k] * B[b*b_batch_rows + j, k].
+// Planes are row-major [rows_total, k_pad] fp16 (k_pad % 64 == 0, m_pad % 128 == 0, n_pad % 64 == 0, zero padded).
+struct TcGemm {
+  const void *Ah, *Al, *Bh, *Bl;
+  long long a_rows_total, b_rows_total;
+  int a_batch_rows, b_batch_rows, batch;
+  int m, n, m_pad, n_pad, k_pad;
+  const float *a_scal, *b_scal;   // device {scale, 1/scale}
+  float* C; long long c_batch_stride; int ldc;   // optional fp32 output (unscaled values)
+  double* sq_out;                                // optional: += sum of squares of C
+};
+int tc_gemm(const TcGemm& g, cudaStream_t st);
 
 struct TcApplyWork {
   TcCondWork kk;   // planes of the matrix the conditional GEMM consumes (Kuf rows for conv, Kzx rows for svgp)

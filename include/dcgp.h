@@ -60,6 +60,8 @@ typedef struct {
 
 const char* dcgp_last_error(void);
 int dcgp_version(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py reports it as gpu_launches) */
+long long dcgp_launch_count(void);
 
 /* views.py:56-68 FullView._patch_count/_patch_length/_out_image_size */
 int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH_host, int* OW_host, int* P_host, int* L_host);
