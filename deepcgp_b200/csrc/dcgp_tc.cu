@@ -463,7 +463,7 @@ int tc_gemm(const TcGemm& g, cudaStream_t st) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.nkb = g.k_pad / kBK;
-  p.m_tiles = g.m_pad / kBM; p.n_tiles = g.n_pad / BN;
+  p.m_tiles = ceil_div(g.m_pad, kBM); p.n_tiles = g.n_pad / BN;   // a 128-row box may run past a batch / the tensor: extra rows are discarded
   p.n_items = g.batch * p.m_tiles * p.n_tiles;
   p.a_batch_rows = g.a_batch_rows; p.b_batch_rows = g.b_batch_rows;
   p.m_valid = g.m; p.n_valid = g.n;
@@ -707,6 +707,7 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
   g.batch = R; g.m = M; g.n = M; g.m_pad = Mp; g.n_pad = Mp; g.k_pad = Mp;
   g.a_scal = t.scal + 4; g.b_scal = t.scal + 6;
   g.C = t.Wr32; g.c_batch_stride = (long long)Mp * Mp; g.ldc = Mp;
+  if (M != Mp) cudaMemsetAsync(t.Wr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);   // padding must not poison the max scan
   if ((rc = tc_gemm(g, st))) return rc;
   if (Lpinv) {
     if ((rc = pack_planes_f64(Lpinv, ldp, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 8, t.Lph, t.Lpl, st))) return rc;

@@ -328,7 +328,7 @@ def test_prior_recovery_full_size(algo):
     assert mean.shape == (64, 196 * 10)
     assert float(mean.abs().max()) == 0.0 or float(mean.abs().max()) < 1e-6
     assert float((var - 5.0).abs().max()) <= 1e-4 * 5.0 + 1e-4 * 5.0
-    assert abs(float(layer.KL().item())) < 1e-6
+    assert abs(float(layer.KL().item())) < (1e-6 if algo == "simt" else 5e-3)    # terms of size R*M = 5120 cancel
 
 
 @pytest.mark.parametrize("algo", ALGOS)
