@@ -27,6 +27,7 @@ struct GemmF64 {
   double* C; int ldc; long long strideC;
   double alpha, beta;
   int batch;
+  int lowerC;   // only output tiles that touch the lower triangle are computed (symmetric rank-k updates)
 };
 int gemm_f64(const GemmF64& g, cudaStream_t st);
 

@@ -30,13 +30,42 @@ int check_launch(const char* what, int n_launched) {
 }
 
 // ------------------------------------------------------------------------------------------ GEMM
+// 64x64 output tile, 16-deep k-slices, 4x4 outputs per thread; the next slice's global loads are issued into registers
+// before the current slice is consumed (software double buffering) because these GEMMs are small and latency-bound.
+__device__ __forceinline__ void gemm_f64_fetch(const GemmF64& g, const double* __restrict__ A, const double* __restrict__ B,
+                                               int i0, int j0, int k0, int tid, double (&ra)[4], double (&rb)[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int idx = tid + e * 256;
+    int i, kk;
+    if (!g.transA) { i = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; i = idx & 63; }
+    const int gi = i0 + i, gk = k0 + kk;
+    double v = 0.0;
+    if (gi < g.m && gk < g.k) {
+      const int r = g.transA ? gk : gi, c = g.transA ? gi : gk;
+      if (!g.lowerA || c <= r) v = A[(long long)r * g.lda + c];
+    }
+    ra[e] = v;
+    int j, kb;
+    if (!g.transB) { kb = idx >> 6; j = idx & 63; } else { j = idx >> 4; kb = idx & 15; }
+    const int gj = j0 + j, gkb = k0 + kb;
+    double w = 0.0;
+    if (gj < g.n && gkb < g.k) {
+      const int r = g.transB ? gj : gkb, c = g.transB ? gkb : gj;
+      if (!g.lowerB || c <= r) w = B[(long long)r * g.ldb + c];
+    }
+    rb[e] = w;
+  }
+}
+
 __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
   __shared__ double As[16][64 + 2];
   __shared__ double Bs[16][64 + 2];
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  if (g.lowerC && j0 > i0 + 63) return;   // output tile strictly above the diagonal: not needed
   const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
   const double* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
   double* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double acc[4][4];
 #pragma unroll
@@ -44,39 +73,22 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
 
-  for (int k0 = 0; k0 < g.k; k0 += 16) {
-    // whole-tile skips for triangular operands (block-uniform)
-    if (g.lowerA) {
-      if (!g.transA && k0 > i0 + 63) break;          // A[i][k], k <= i
-      if (g.transA && k0 + 15 < i0) continue;        // A[k][i], i <= k
-    }
-    if (g.lowerB) {
-      if (!g.transB && k0 + 15 < j0) continue;       // B[k][j], j <= k
-      if (g.transB && k0 > j0 + 63) break;           // B[j][k], k <= j
-    }
+  // k-range that can be non-zero given triangular operands (block-uniform)
+  int kbeg = 0, kend = g.k;
+  if (g.lowerA) { if (!g.transA) kend = min(kend, i0 + 64); else kbeg = max(kbeg, i0 & ~15); }
+  if (g.lowerB) { if (!g.transB) kbeg = max(kbeg, j0 & ~15); else kend = min(kend, j0 + 64); }
+
+  double ra[4], rb[4];
+  if (kbeg < kend) gemm_f64_fetch(g, A, B, i0, j0, kbeg, tid, ra, rb);
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = tid + e * 256;
-      int i, kk;
-      if (!g.transA) { i = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; i = idx & 63; }
-      const int gi = i0 + i, gk = k0 + kk;
-      double v = 0.0;
-      if (gi < g.m && gk < g.k) {
-        const int r = g.transA ? gk : gi, c = g.transA ? gi : gk;
-        if (!g.lowerA || c <= r) v = A[(long long)r * g.lda + c];
-      }
-      As[kk][i] = v;
-      int j, kb;
-      if (!g.transB) { kb = idx >> 6; j = idx & 63; } else { j = idx >> 4; kb = idx & 15; }
-      const int gj = j0 + j, gkb = k0 + kb;
-      double w = 0.0;
-      if (gj < g.n && gkb < g.k) {
-        const int r = g.transB ? gj : gkb, c = g.transB ? gkb : gj;
-        if (!g.lowerB || c <= r) w = B[(long long)r * g.ldb + c];
-      }
-      Bs[kb][j] = w;
+      if (!g.transA) As[idx & 15][idx >> 4] = ra[e]; else As[idx >> 6][idx & 63] = ra[e];
+      if (!g.transB) Bs[idx >> 6][idx & 63] = rb[e]; else Bs[idx & 15][idx >> 4] = rb[e];
     }
     __syncthreads();
+    if (k0 + 16 < kend) gemm_f64_fetch(g, A, B, i0, j0, k0 + 16, tid, ra, rb);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       double a[4], b[4];
@@ -288,6 +300,9 @@ size_t potrf_ws_bytes(int M) { return (size_t)ceil_div(M, NB) * NB * NB * sizeof
 
 constexpr int kDiagSmem = 3 * NB * (NB + 1) * sizeof(double);
 
+// Right-looking blocked Cholesky: per 64-column panel (1) factor + invert the diagonal block in one CTA, (2) solve the
+// panel below it, (3) rank-64 update of the trailing lower triangle -- a wide, shallow GEMM (k = 64) that fills the machine,
+// where a left-looking update would be a narrow GEMM with a long sequential k loop.
 int potrf_f64(double* A, int lda, int M, double* invD, int* info, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -298,20 +313,19 @@ int potrf_f64(double* A, int lda, int M, double* invD, int* info, cudaStream_t s
   const int nblk = ceil_div(M, NB);
   for (int jb = 0; jb < nblk; ++jb) {
     const int j0 = jb * NB, nb = (M - j0 < NB) ? (M - j0) : NB;
-    if (j0 > 0) {  // left-looking update of the block column with everything already factored
-      GemmF64 g{};
-      g.m = M - j0; g.n = nb; g.k = j0;
-      g.A = A + (long long)j0 * lda; g.lda = lda; g.transA = 0;
-      g.B = A + (long long)j0 * lda; g.ldb = lda; g.transB = 1;
-      g.C = A + (long long)j0 * lda + j0; g.ldc = lda;
-      g.alpha = -1.0; g.beta = 1.0; g.batch = 1;
+    potrf_diag_kernel<<<1, 256, kDiagSmem, st>>>(A, lda, j0, nb, invD + (size_t)jb * NB * NB, info);
+    const int rows_below = M - j0 - nb;
+    if (rows_below > 0) {
+      trsm_panel_kernel<<<ceil_div(rows_below, NB), 256, kDiagSmem, st>>>(A, lda, M, j0, nb, invD + (size_t)jb * NB * NB);
+      GemmF64 g{};   // A22 -= P P^T  (lower tiles only)
+      g.m = g.n = rows_below; g.k = nb;
+      g.A = A + (long long)(j0 + nb) * lda + j0; g.lda = lda; g.transA = 0;
+      g.B = g.A; g.ldb = lda; g.transB = 1;
+      g.C = A + (long long)(j0 + nb) * lda + (j0 + nb); g.ldc = lda;
+      g.alpha = -1.0; g.beta = 1.0; g.batch = 1; g.lowerC = 1;
       int rc = gemm_f64(g, st);
       if (rc) return rc;
     }
-    potrf_diag_kernel<<<1, 256, kDiagSmem, st>>>(A, lda, j0, nb, invD + (size_t)jb * NB * NB, info);
-    const int rows_below = M - j0 - nb;
-    if (rows_below > 0)
-      trsm_panel_kernel<<<ceil_div(rows_below, NB), 256, kDiagSmem, st>>>(A, lda, M, j0, nb, invD + (size_t)jb * NB * NB);
   }
   zero_upper_kernel<<<dim3(ceil_div(M, 256), M), 256, 0, st>>>(A, lda, M);
   return check_launch("potrf_f64", 2 * nblk);   // nblk diag + (nblk-1) panel solves + zero_upper

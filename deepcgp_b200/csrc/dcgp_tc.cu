@@ -731,7 +731,270 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
   return check_launch("tc_build_operands", 2);
 }
 
-int tc_pack_z(const TcPrep&, const double*, int, int, double, cudaStream_t) { return DCGP_OK; }  // used by the tensor-core Kuf kernel
+// ============================================================================================ K-A: Kuf on tensor cores
+// Fused im2col + squared distance + RBF (layers.py:23-32, kernels.py:117-123):
+//   D[t, m] = sum_l xs[t, l] * zs[m, l]        (xs = patch / lengthscale gathered straight from the NHWC image, zs = Z / ls)
+//   k[t, m] = variance * exp(-0.5 * (|xs_t|^2 + |zs_m|^2 - 2 D[t, m]))        (GPflow's expansion form of the RBF)
+// Roles: 4 gather warps (im2col rows -> split fp16 -> SWIZZLE_128B smem, + the TMA loads of the Z planes), 1 MMA warp,
+// 4 epilogue warps (TMEM -> exp -> split-fp16 planes of K, the A operand of the conditional GEMM).  Patches never touch HBM.
+constexpr float kXScale = 256.f;             // fixed power-of-two pre-scale of xs and zs before the fp16 split
+constexpr int kKufThreads = 288;             // warps 0-3 gather, warp 4 MMA, warps 5-8 epilogue
+
+struct KufParams {
+  const float* X;      // [n_rows, HWC]
+  View v;
+  int T;               // n_rows * P
+  int M, Mp;
+  int njt;             // Mp / BN
+  int n_items;         // t-tiles * njt
+  int nkb;             // ceil(L / 64)
+  float inv_ls, variance;
+  const float* zz;     // [Mp] |zs_m|^2
+  const float* kscal;  // {scale, 1/scale} of the output planes
+  __half* Kh; __half* Kl;   // [Tpad, Mp]
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kKufThreads, 1)
+kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant__ CUtensorMap tmZ_lo, KufParams p) {
+  using Cfg = CondCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
+  float* xx_s = (float*)(tmem_base_smem + 4);     // [4][128] squared norms of the tile's patches (ring over tiles)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.v.L;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmZ_hi); tma_prefetch_desc(&tmZ_lo);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }   // 4 gather warps + TMA
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_smem;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ gather: one patch row per thread
+    const int r = threadIdx.x;                      // 0..127
+    const int fC = p.v.f * p.v.C, rowstride = p.v.W * p.v.C;
+    int stage = 0; uint32_t phase = 0; uint32_t tile = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
+      const int tt = item / p.njt, jt = item - tt * p.njt;
+      const int t = tt * kBM + r;
+      const bool valid = t < p.T;
+      const float* src = p.X;
+      if (valid) {
+        const int n = t / p.v.P, pp = t - n * p.v.P;
+        src += (long long)n * p.v.HWC + p.v.patch_base(pp);
+      }
+      float xx = 0.f;
+      int dy = 0, q = 0;                            // patch element l = dy * fC + q
+      for (int kb = 0; kb < p.nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::kStageBytes;
+        if (threadIdx.x == 0) {
+          mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageB);
+          tma_load_2d(st + 2 * Cfg::kStageA, &tmZ_hi, &full_bar[stage], kb * kBK, jt * BN);
+          tma_load_2d(st + 2 * Cfg::kStageA + Cfg::kStageB, &tmZ_lo, &full_bar[stage], kb * kBK, jt * BN);
+        }
+        const int l0 = kb * kBK;
+        int nchunk = (L - l0 + 7) >> 3;             // 16-byte chunks (8 elements) that hold data
+        nchunk = nchunk > 8 ? 8 : ((nchunk + 1) & ~1);   // whole 16-element k-steps
+        uint8_t* rowh = st + (r >> 3) * 1024 + (r & 7) * 128;
+        uint8_t* rowl = rowh + Cfg::kStageA;
+        for (int c = 0; c < nchunk; ++c) {
+          __half hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x = 0.f;
+            if (valid && l0 + c * 8 + e < L) {
+              x = __ldg(src + dy * rowstride + q) * p.inv_ls;
+              if (++q == fC) { q = 0; ++dy; }
+            }
+            xx = fmaf(x, x, xx);
+            const float xsx = x * kXScale;
+            hi[e] = __float2half_rn(xsx);
+            lo[e] = __float2half_rn(xsx - __half2float(hi[e]));
+          }
+          const int pc = (c ^ (r & 7)) * 16;        // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(rowh + pc) = *reinterpret_cast<uint4*>(hi);
+          *reinterpret_cast<uint4*>(rowl + pc) = *reinterpret_cast<uint4*>(lo);
+        }
+        if (kb == p.nkb - 1) xx_s[(tile & 3) * kBM + r] = xx;
+        fence_proxy_async();                        // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BN);
+      int stage = 0; uint32_t phase = 0; uint32_t tile = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
+        const uint32_t buf = tile & 1, use = tile >> 1;
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t a_lo = a_hi + Cfg::kStageA;
+          const uint32_t b_hi = a_hi + 2 * Cfg::kStageA;
+          const uint32_t b_lo = b_hi + Cfg::kStageB;
+          const uint64_t dah = make_sw128_desc(a_hi), dal = make_sw128_desc(a_lo);
+          const uint64_t dbh = make_sw128_desc(b_hi), dbl = make_sw128_desc(b_lo);
+          int ksteps = (L - kb * kBK + 15) >> 4;
+          ksteps = ksteps > 4 ? 4 : ksteps;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+            umma_f16(d_tmem, dal + koff, dbh + koff, idesc, (kb | k) != 0);
+            umma_f16(d_tmem, dah + koff, dbl + koff, idesc, 1);
+            umma_f16(d_tmem, dah + koff, dbh + koff, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: exp + split, one patch row per thread
+    const int q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float ks = p.kscal[0] * p.variance;
+    const float dscale = 2.f / (kXScale * kXScale);
+    uint32_t tile = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
+      const int tt = item / p.njt, jt = item - tt * p.njt;
+      const int row = q * 32 + lane;
+      const long long t = (long long)tt * kBM + row;
+      const uint32_t buf = tile & 1, use = tile >> 1;
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      const float xx = xx_s[(tile & 3) * kBM + row];
+      const bool valid = t < p.T;
+      const uint32_t taddr = tmem_base + lane_base + buf * BN;
+      __half* oh = p.Kh + t * p.Mp + jt * BN;
+      __half* ol = p.Kl + t * p.Mp + jt * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld_32x32(taddr + c, v);
+        __align__(16) __half hi[32];
+        __align__(16) __half lo[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int m = jt * BN + c + i;
+          const float d = xx + __ldg(p.zz + m) - dscale * v[i];
+          const float k = (valid && m < p.M) ? ks * __expf(-0.5f * d) : 0.f;
+          hi[i] = __float2half_rn(k);
+          lo[i] = __float2half_rn(k - __half2float(hi[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          reinterpret_cast<uint4*>(oh + c)[i] = reinterpret_cast<uint4*>(hi)[i];
+          reinterpret_cast<uint4*>(ol + c)[i] = reinterpret_cast<uint4*>(lo)[i];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// Z / lengthscale (x kXScale) as split-fp16 planes [Mp, Lp] (Lp = ceil(L/64)*64, zero padded) and |zs_m|^2 in fp32.
+__global__ void pack_z_f16_kernel(const double* __restrict__ Z, int M, int Mp, int L, int Lp, double inv_ls,
+                                  __half* __restrict__ Zh, __half* __restrict__ Zl, float* __restrict__ zz) {
+  const int m = blockIdx.x;
+  double acc = 0.0;
+  for (int l = threadIdx.x; l < Lp; l += blockDim.x) {
+    double v = 0.0;
+    if (m < M && l < L) v = Z[(long long)m * L + l] * inv_ls;
+    acc += v * v;
+    const double vs = v * (double)kXScale;
+    const __half hi = __float2half_rn((float)vs);
+    Zh[(long long)m * Lp + l] = hi;
+    Zl[(long long)m * Lp + l] = __float2half_rn((float)(vs - (double)__half2float(hi)));
+  }
+  __shared__ double sh[4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) zz[m] = (float)(sh[0] + sh[1] + sh[2] + sh[3]);
+}
+
+int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st) {
+  pack_z_f16_kernel<<<t.Mp, 128, 0, st>>>(Z, M, t.Mp, L, t.Lp, inv_ls, (__half*)t.Zh, (__half*)t.Zl, t.zz);
+  return check_launch("pack_z_f16");
+}
+
+template <int BN>
+static int launch_kuf_tc(const TcPrep& prep, const View& v, const float* X, int n_rows, float variance, float inv_ls,
+                         const float* kscal, void* Kh, void* Kl, cudaStream_t st) {
+  using Cfg = CondCfg<BN>;
+  CUtensorMap tmZh, tmZl;
+  int rc;
+  if ((rc = make_tmap_f16(&tmZh, prep.Zh, prep.Mp, prep.Lp, BN))) return rc;
+  if ((rc = make_tmap_f16(&tmZl, prep.Zl, prep.Mp, prep.Lp, BN))) return rc;
+  KufParams p;
+  p.X = X; p.v = v; p.T = n_rows * v.P; p.M = prep.M; p.Mp = prep.Mp; p.njt = prep.Mp / BN;
+  p.n_items = ceil_div(p.T, kBM) * p.njt;
+  p.nkb = ceil_div(v.L, kBK);
+  p.inv_ls = inv_ls; p.variance = variance; p.zz = prep.zz; p.kscal = kscal; p.Kh = (__half*)Kh; p.Kl = (__half*)Kl;
+  constexpr int smem_bytes = Cfg::kSmemBytes + 4 * kBM * 4;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(kuf_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { set_error("kuf_tc smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
+    attr = true;
+  }
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  kuf_tc_kernel<BN><<<grid, kKufThreads, smem_bytes, st>>>(tmZh, tmZl, p);
+  return check_launch("kuf_tc");
+}
+
+// Planes [Tpad, Mp] of variance * exp(...) * kscal[0] for all n_rows * P patches.
+int tc_kuf(const TcPrep& prep, const View& v, const float* X, int n_rows, float variance, float inv_ls, const float* kscal,
+           void* Kh, void* Kl, cudaStream_t st) {
+  if (prep.Mp % 256 == 0) return launch_kuf_tc<256>(prep, v, X, n_rows, variance, inv_ls, kscal, Kh, Kl, st);
+  if (prep.Mp % 128 == 0) return launch_kuf_tc<128>(prep, v, X, n_rows, variance, inv_ls, kscal, Kh, Kl, st);
+  return launch_kuf_tc<64>(prep, v, X, n_rows, variance, inv_ls, kscal, Kh, Kl, st);
+}
+
+// kernels.py:127-133 on the planes: Kzx[n, m] = (1/P) sum_p w_p K[(n*P+p), m], fp32 (unscaled) [n_rows, Mp]
+__global__ void patch_mean_planes_kernel(const __half* __restrict__ Kh, const __half* __restrict__ Kl, int P, int Mp,
+                                         const double* __restrict__ w, const float* __restrict__ kscal, float* __restrict__ out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (m >= Mp) return;
+  float acc = 0.f;
+  const long long base = (long long)n * P * Mp + m;
+  for (int pp = 0; pp < P; ++pp) {
+    const float k = __half2float(Kh[base + (long long)pp * Mp]) + __half2float(Kl[base + (long long)pp * Mp]);
+    acc = fmaf(w ? (float)w[pp] : 1.f, k, acc);
+  }
+  out[(long long)n * Mp + m] = acc * kscal[1] / (float)P;
+}
 
 void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf) {
   memset(&w, 0, sizeof(w));
@@ -757,13 +1020,18 @@ int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStrea
 void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, void* buf) {
   memset(&a, 0, sizeof(a));
   Carve2 c(buf);
-  // conv: the Kuf kernel writes fp16 planes of the [Tk, Mp] kernel matrix directly.
-  // svgp: the patch-level matrix stays fp32 (it is averaged over patches first); only Kzx [T, Mp] is split.
-  const size_t rows = (kind == DCGP_LAYER_CONV) ? Tk : T;
-  a.kk.Tpad = align_up(rows, kBM);
+  // conv: the Kuf kernel writes the planes of the [Tk, Mp] kernel matrix the conditional GEMM consumes.
+  // svgp: the same planes are averaged over patches into Kzx [T, Mp] (fp32), which is then split into its own planes.
+  a.kk.Tpad = align_up(Tk, kBM);
   a.kk.Kh = c.take(a.kk.Tpad * Mp * 2);
   a.kk.Kl = c.take(a.kk.Tpad * Mp * 2);
   a.kk.kscal = (float*)c.take(8 * 4);
+  if (kind != DCGP_LAYER_CONV) {
+    a.kz.Tpad = align_up(T, kBM);
+    a.kz.Kh = c.take(a.kz.Tpad * Mp * 2);
+    a.kz.Kl = c.take(a.kz.Tpad * Mp * 2);
+    a.kz.kscal = (float*)c.take(8 * 4);
+  }
   a.bytes = align_up(c.off, 1024);
 }
 
@@ -773,23 +1041,19 @@ int launch_kuf_simt_planes(const float* X, const View& v, int n_rows, const floa
 int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const float* zs,
                    float* Kt32, const double* patch_weights, const float* X, int n_rows, float* Kzx, float* acc, float* mean_t,
                    cudaStream_t st) {
-  const int Mp = prep.Mp, M = prep.M, R = prep.R;
+  const int Mp = prep.Mp, R = prep.R;
   const float variance = (float)d->variance, inv_ls = (float)(1.0 / d->lengthscale);
-  if (d->kind == DCGP_LAYER_CONV) {
-    const int T = n_rows * v.P;
-    set_scale_kernel<<<1, 1, 0, st>>>(variance, a.kk.kscal);      // RBF values lie in (0, variance]
-    check_launch("set_scale");
-    int rc = launch_kuf_simt_planes(X, v, n_rows, zs, M, variance, inv_ls, Mp, a.kk.kscal, a.kk.Kh, a.kk.Kl, (long long)a.kk.Tpad, st);
-    if (rc) return rc;
-    return tc_cond(prep, a.kk, T, Mp, R, acc, mean_t, st);
-  }
-  int rc = launch_kuf_simt(X, v, n_rows, zs, M, variance, inv_ls, 1, Mp, Kt32, st);
+  (void)zs; (void)Kt32;
+  set_scale_kernel<<<1, 1, 0, st>>>(variance, a.kk.kscal);      // RBF values lie in (0, variance]
+  check_launch("set_scale");
+  int rc = tc_kuf(prep, v, X, n_rows, variance, inv_ls, a.kk.kscal, a.kk.Kh, a.kk.Kl, st);   // layers.py:112 / kernels.py:123
   if (rc) return rc;
-  rc = launch_patch_mean(Kt32, n_rows, v.P, Mp, M, patch_weights, 0, Mp, Kzx, st);
-  if (rc) return rc;
-  rc = tc_split_rows(Kzx, n_rows, Mp, a.kk, st);
-  if (rc) return rc;
-  return tc_cond(prep, a.kk, n_rows, Mp, R, acc, mean_t, st);
+  if (d->kind == DCGP_LAYER_CONV) return tc_cond(prep, a.kk, n_rows * v.P, Mp, R, acc, mean_t, st);
+  patch_mean_planes_kernel<<<dim3(ceil_div(Mp, 128), n_rows), 128, 0, st>>>((const __half*)a.kk.Kh, (const __half*)a.kk.Kl, v.P, Mp,
+                                                                          patch_weights, a.kk.kscal, Kzx);
+  if ((rc = check_launch("patch_mean_planes"))) return rc;
+  if ((rc = tc_split_rows(Kzx, n_rows, Mp, a.kz, st))) return rc;
+  return tc_cond(prep, a.kz, n_rows, Mp, R, acc, mean_t, st);
 }
 
 }  // namespace dcgp

@@ -53,9 +53,12 @@ struct TcGemm {
 int tc_gemm(const TcGemm& g, cudaStream_t st);
 
 struct TcApplyWork {
-  TcCondWork kk;   // planes of the matrix the conditional GEMM consumes (Kuf rows for conv, Kzx rows for svgp)
+  TcCondWork kk;   // planes of the patch-level kernel matrix (Kuf rows)
+  TcCondWork kz;   // svgp only: planes of the image-level Kzx rows
   size_t bytes;
 };
+int tc_kuf(const TcPrep& prep, const View& v, const float* X, int n_rows, float variance, float inv_ls, const float* kscal,
+           void* Kh, void* Kl, cudaStream_t st);
 void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, void* buf);
 int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const float* zs,
                    float* Kt32, const double* patch_weights, const float* X, int n_rows, float* Kzx, float* acc,

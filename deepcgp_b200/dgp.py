@@ -40,6 +40,7 @@ class DGP_Base(object):
         self._kls = torch.zeros(len(self.layers), dtype=torch.float64, device=self.device)
         self._sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._elbo = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self._side = None
 
     # ------------------------------------------------------------------ DS/dgp.py:61-76
     def propagate(self, X, full_cov=False, S=1, zs=None):
@@ -76,8 +77,18 @@ class DGP_Base(object):
         X = _lib.f32(X, self.device)
         N = X.shape[0]
         S = self.num_samples
-        for i, layer in enumerate(self.layers):          # minibatch-independent work once per step
-            layer.prepare()
+        # Minibatch-independent ("M-only") work once per step.  It is latency-bound (Cholesky chains on a handful of
+        # CTAs) and independent across layers, so each layer's chain runs on its own side stream, concurrently with
+        # the other layers' chains and with the minibatch-sized kernels of earlier layers on the main stream.
+        main = torch.cuda.current_stream(self.device)
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=self.device) for _ in self.layers]
+        for layer, side in zip(self.layers, self._side):
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                layer.prepare()
+                layer._ready = torch.cuda.Event()
+                layer._ready.record(side)
             layer._hold = True
         try:
             Fmean, Fvar = self._build_predict(X, full_cov=False, S=S, zs=zs)
@@ -85,10 +96,12 @@ class DGP_Base(object):
             lik = self.likelihood.likelihood
             lik.variational_expectations(Fmean.reshape(S * N, K), Fvar.reshape(S * N, K), Y, S=S, out_sum=self._sum)
             for i, layer in enumerate(self.layers):
+                main.wait_event(layer._ready)
                 self._kls[i:i + 1].copy_(layer._kl)
         finally:
             for layer in self.layers:
                 layer._hold = False
+                layer._ready = None
         _lib.check(_lib.lib.dcgp_elbo(_lib.ptr(self._sum), S, float(self.num_data), float(n_global or N),
                                       _lib.ptr(self._kls), len(self.layers), _lib.ptr(self._elbo), _lib.stream()))
         return self._elbo[0]

@@ -149,6 +149,7 @@ class _PatchGPLayer(Layer):
         self._kl = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._info = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._hold = False
+        self._ready = None      # CUDA event recorded after prepare() when it ran on a side stream
         self.algo = None
         if q_sqrt is None:
             if not self.white:                                              # layers.py:154-158 / DS/layers.py:168-174
@@ -197,6 +198,8 @@ class _PatchGPLayer(Layer):
     def _conditional(self, X, n_rep=1, z=None):
         if not self._hold:
             self.prepare()
+        elif self._ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._ready)
         d = self._desc()
         X = _lib.f32(X, self.device)
         n_rows = X.shape[0]
