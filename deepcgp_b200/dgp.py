@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .dist import allreduce_sum_
 from .layers import TiledInput
 from .likelihoods import BroadcastingLikelihood
 
@@ -102,6 +103,8 @@ class DGP_Base(object):
             for layer in self.layers:
                 layer._hold = False
                 layer._ready = None
+        if n_global is not None and n_global != N:
+            allreduce_sum_(self._sum)        # image-sharded step: the data term is a sum over all ranks' images
         _lib.check(_lib.lib.dcgp_elbo(_lib.ptr(self._sum), S, float(self.num_data), float(n_global or N),
                                       _lib.ptr(self._kls), len(self.layers), _lib.ptr(self._elbo), _lib.stream()))
         return self._elbo[0]
