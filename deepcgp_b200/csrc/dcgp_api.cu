@@ -326,8 +326,16 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
     Lpinv = w.Lpinv;
   }
   if (algo == DCGP_ALGO_TC) {
+    if (d->white) {   // Q_0 = Kuu^-1 is needed by the backward operands even when G = Lm^-1
+      GemmF64 g{};
+      g.m = g.n = g.k = M;
+      g.A = w.Linv; g.lda = w.Mq; g.transA = 1; g.lowerA = 1;
+      g.B = w.Linv; g.ldb = w.Mq; g.lowerB = 1;
+      g.C = w.Kinv; g.ldc = M; g.alpha = 1.0; g.batch = 1;
+      DCGP_TRY(gemm_f64(g, st));
+    }
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, st));
+                               w.beta, w.sc + 1, w.Kinv, st));
     DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
     return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
   }
@@ -400,6 +408,66 @@ int dcgp_layer_apply(const dcgp_layer_desc* d, const void* prep_buf, const doubl
   if (!conv) DCGP_TRY(launch_kdiag(X, v, n_rows, patch_weights, variance, inv_ls * inv_ls, a.kdiag, st));  // kernels.py:106-115
   return launch_finalize(a.acc, a.mean_t, T, p.R, variance, conv ? nullptr : a.kdiag, n_rep, z, (float)d->jitter, mean, var,
                          sample, st);
+}
+
+// ---------------------------------------------------------------------------------------------- layer backward
+static void bwd_dims(const dcgp_layer_desc* d, int n_rows, View& v, size_t& Tk, size_t& T, int& Mp) {
+  v = make_view(d->H, d->W, d->C, d->f, d->s);
+  Mp = (int)align_up(d->M, 64);
+  Tk = (size_t)n_rows * v.P;
+  T = (d->kind == DCGP_LAYER_CONV) ? Tk : (size_t)n_rows;
+}
+
+size_t dcgp_backward_workspace_bytes(const dcgp_layer_desc* d, int n_rows, int n_rep) {
+  (void)n_rep;
+  if (check_desc(d) || n_rows < 1) return 0;
+  View v; size_t Tk, T; int Mp;
+  bwd_dims(d, n_rows, v, Tk, T, Mp);
+  TcBwdWork b;
+  tc_carve_bwd(b, d->kind, d->M, Mp, d->R, v.L, Tk, T, v.P, nullptr);
+  return b.bytes + 1024;
+}
+
+int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep_buf, const void* apply_ws, const double* Z,
+                        const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
+                        const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, void* ws,
+                        size_t ws_bytes, void* stream) {
+  DCGP_TRY(check_desc(d));
+  if (!prep_buf || !apply_ws || !Z || !X || !g_mean || !g_var || !gQB || !gZ || !gscal || n_rows < 1 || n_rep < 1) {
+    set_error("layer_backward: bad argument");
+    return DCGP_ERR_ARG;
+  }
+  if (d->kind == DCGP_LAYER_SVGP_CONV && !gw) { set_error("layer_backward: gw required for the ConvKernel layer"); return DCGP_ERR_ARG; }
+  View v; size_t Tk, T; int Mp;
+  bwd_dims(d, n_rows, v, Tk, T, Mp);
+  TcBwdWork b;
+  void* wsa = (void*)align_up((size_t)ws, 1024);
+  tc_carve_bwd(b, d->kind, d->M, Mp, d->R, v.L, Tk, T, v.P, wsa);
+  if (!ws || ws_bytes < b.bytes + 1024) { set_error("layer_backward: workspace too small (%zu < %zu)", ws_bytes, b.bytes + 1024); return DCGP_ERR_WORKSPACE; }
+  Prep p = carve_prep(d, const_cast<void*>(prep_buf));
+  ApplyWork a = carve_apply(d, n_rows, const_cast<void*>(apply_ws));
+  return tc_layer_backward(d, v, p.tc, a.tc, b, Z, patch_weights, X, n_rows, n_rep, g_mean, g_var, gX, gQB, gZ, gscal, gw,
+                           (cudaStream_t)stream);
+}
+
+int dcgp_multiclass_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,
+                                double coef, float* gmu, float* gvar, void* stream) {
+  if (!Fmu || !Fvar || !Y || !gmu || !gvar || S < 1 || N < 1) { set_error("varexp_grad: bad argument"); return DCGP_ERR_ARG; }
+  return launch_varexp_grad(Fmu, Fvar, Y, S, N, K, epsilon, coef, gmu, gvar, (cudaStream_t)stream);
+}
+
+int dcgp_sample_backward(const float* gF, const float* z, const float* var, size_t n, double jitter, float* g_mean,
+                         float* g_var, void* stream) {
+  if (!gF || !z || !var || !g_mean || !g_var) { set_error("sample_backward: null argument"); return DCGP_ERR_ARG; }
+  if (n == 0) return DCGP_OK;
+  return launch_sample_backward(gF, z, var, n, (float)jitter, g_mean, g_var, (cudaStream_t)stream);
+}
+
+int dcgp_adam(double* param, const double* grad, double* m, double* v, size_t n, double lr, double beta1, double beta2,
+              double eps, int step, int maximize, void* stream) {
+  if (!param || !grad || !m || !v || step < 1) { set_error("adam: bad argument"); return DCGP_ERR_ARG; }
+  if (n == 0) return DCGP_OK;
+  return launch_adam(param, grad, m, v, n, lr, beta1, beta2, eps, step, maximize, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------- ConvKernel API mirror

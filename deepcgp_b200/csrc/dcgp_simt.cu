@@ -458,6 +458,88 @@ __global__ void __launch_bounds__(1024) sum_f64_kernel(const double* __restrict_
   }
 }
 
+// Gradient of the expected log-likelihood w.r.t. Fmu, Fvar (times `coef`), same quadrature as varexp_kernel:
+//   p = sum_g w_g prod_{k!=y} c(u_gk),  u_gk = (mu_y + x_g sqrt(2 v_y) - mu_k) / sqrt(v_k),  c = Phi*(1-2e-4)+1e-4
+__global__ void __launch_bounds__(128) varexp_grad_kernel(const float* __restrict__ Fmu, const float* __restrict__ Fvar,
+                                                          const int32_t* __restrict__ Y, int SN, int N, int K, double dlog,
+                                                          double coef, float* __restrict__ gmu, float* __restrict__ gvar) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= SN) return;
+  const int y = Y[i % N];
+  double mu[16], isd[16], vk[16], dmu[16], dv[16];
+  bool vclip[16];
+  for (int k = 0; k < K; ++k) {
+    mu[k] = (double)Fmu[(long long)i * K + k];
+    const double v = (double)Fvar[(long long)i * K + k];
+    vclip[k] = !(v > 1e-10);
+    vk[k] = fmax(v, 1e-10);
+    isd[k] = 1.0 / sqrt(vk[k]);
+    dmu[k] = 0.0;
+    dv[k] = 0.0;
+  }
+  const double vy2 = 2.0 * (double)Fvar[(long long)i * K + y];
+  const bool yclip = !(vy2 > 1e-10);
+  const double sd2 = sqrt(fmax(vy2, 1e-10));
+  for (int g = 0; g < 20; ++g) {
+    const double x = mu[y] + c_gh_x[g] * sd2;
+    double c[16], u[16], prod = 1.0;
+    for (int k = 0; k < K; ++k) {
+      if (k == y) continue;
+      u[k] = (x - mu[k]) * isd[k];
+      c[k] = 0.5 * (1.0 + erf(u[k] * 0.70710678118654752440)) * (1.0 - 2e-4) + 1e-4;
+      prod *= c[k];
+    }
+    for (int k = 0; k < K; ++k) {
+      if (k == y) continue;
+      const double phi = 0.3989422804014327 * exp(-0.5 * u[k] * u[k]) * (1.0 - 2e-4);
+      const double A = c_gh_w[g] * (prod / c[k]) * phi;       // d p / d u_gk (weighted)
+      dmu[k] -= A * isd[k];
+      if (!vclip[k]) dv[k] -= A * u[k] / (2.0 * vk[k]);
+      dmu[y] += A * isd[k];
+      if (!yclip) dv[y] += A * isd[k] * c_gh_x[g] / sd2;       // d x_g / d v_y = gh_x / sqrt(2 v_y)
+    }
+  }
+  const double f = coef * dlog;   // dlog = log(1-eps) - log(eps/(K-1))
+  for (int k = 0; k < K; ++k) {
+    gmu[(long long)i * K + k] = (float)(f * dmu[k]);
+    gvar[(long long)i * K + k] = (float)(f * dv[k]);
+  }
+}
+
+// DS/utils.py:41 backward: F = mean + z sqrt(var + jitter)  ->  g_mean = gF, g_var = gF * z / (2 sqrt(var + jitter))
+__global__ void sample_backward_kernel(const float* __restrict__ gF, const float* __restrict__ z, const float* __restrict__ var,
+                                       size_t n, float jitter, float* __restrict__ g_mean, float* __restrict__ g_var) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const float g = gF[e];
+    g_mean[e] = g;
+    g_var[e] = g * z[e] * 0.5f * rsqrtf(var[e] + jitter);
+  }
+}
+int launch_sample_backward(const float* gF, const float* z, const float* var, size_t n, float jitter, float* g_mean, float* g_var,
+                           cudaStream_t st) {
+  sample_backward_kernel<<<148 * 8, 256, 0, st>>>(gF, z, var, n, jitter, g_mean, g_var);
+  return check_launch("sample_backward");
+}
+
+// Adam (experiment.py:97-99, tf.train.AdamOptimizer semantics) on a flat float64 parameter vector; maximize=1 ascends.
+__global__ void adam_kernel(double* __restrict__ p, const double* __restrict__ g, double* __restrict__ m, double* __restrict__ v,
+                            size_t n, double lr_t, double b1, double b2, double eps, double sign) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const double ge = sign * g[e];
+    const double me = b1 * m[e] + (1.0 - b1) * ge;
+    const double ve = b2 * v[e] + (1.0 - b2) * ge * ge;
+    m[e] = me;
+    v[e] = ve;
+    p[e] -= lr_t * me / (sqrt(ve) + eps);
+  }
+}
+int launch_adam(double* param, const double* grad, double* m, double* v, size_t n, double lr, double b1, double b2, double eps,
+                int step, int maximize, cudaStream_t st) {
+  const double lr_t = lr * sqrt(1.0 - pow(b2, step)) / (1.0 - pow(b1, step));   // TF's bias-corrected step size
+  adam_kernel<<<148 * 4, 256, 0, st>>>(param, grad, m, v, n, lr_t, b1, b2, eps, maximize ? -1.0 : 1.0);
+  return check_launch("adam");
+}
+
 static void gauss_hermite_20(double* x, double* w) {
   // Newton iteration on the orthonormal Hermite recurrence (classic `gauher`), n = 20.
   const int n = 20;
@@ -489,10 +571,34 @@ static void gauss_hermite_20(double* x, double* w) {
   }
 }
 
+static void init_gh();
+int launch_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon, double coef,
+                       float* gmu, float* gvar, cudaStream_t st) {
+  if (K > 16 || K < 2) { set_error("varexp_grad: K must be in [2,16]"); return DCGP_ERR_ARG; }
+  init_gh();
+  const int SN = S * N;
+  varexp_grad_kernel<<<ceil_div(SN, 128), 128, 0, st>>>(Fmu, Fvar, Y, SN, N, K, log(1.0 - epsilon) - log(epsilon / (K - 1.0)), coef,
+                                                        gmu, gvar);
+  return check_launch("varexp_grad");
+}
+
+static void init_gh() {
+  static bool init = false;
+  if (!init) {
+    double x[20], w[20];
+    gauss_hermite_20(x, w);
+    for (int i = 0; i < 20; ++i) w[i] /= sqrt(M_PI);
+    cudaMemcpyToSymbol(c_gh_x, x, sizeof(x));
+    cudaMemcpyToSymbol(c_gh_w, w, sizeof(w));
+    init = true;
+  }
+}
+
 int launch_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon, double* varexp,
                   double* sum, cudaStream_t st) {
   if (K > 16 || K < 2) { set_error("varexp: K must be in [2,16]"); return DCGP_ERR_ARG; }
-  static bool init = false;
+  init_gh();
+  static bool init = true;
   if (!init) {
     double x[20], w[20];
     gauss_hermite_20(x, w);

@@ -154,6 +154,10 @@ struct TcParams {
   long long c_batch_stride;
   int ldc;
   double* sq_out;        // may be null: += sum of squares of all valid C entries
+  float* absmax_out;     // may be null: atomic max of |C| over valid entries
+  int splits;            // split-K: item = (split, batch, it, jn); partial results go to C + split * c_split_stride
+  int nkb_split;         // k-blocks per split
+  long long c_split_stride;
 };
 
 template <int MODE, int BN>
@@ -169,10 +173,23 @@ __device__ __forceinline__ void tile_rows(const TcParams& p, int item, int jt, i
     b_row = blk * p.Mp + jt * BN;
   } else {
     const int per = p.m_tiles * p.n_tiles;
-    const int b = item / per, rem = item - b * per;
+    const int bb = item / per, rem = item - bb * per;
+    const int b = bb % (p.splits > 0 ? (p.n_items / per / p.splits) : 1);
     const int it = rem / p.n_tiles, jn = rem - it * p.n_tiles;
     a_row = b * p.a_batch_rows + it * kBM;
     b_row = b * p.b_batch_rows + jn * BN;
+  }
+}
+// k-block range of an item (split-K for MODE_GEMM)
+template <int MODE>
+__device__ __forceinline__ void item_krange(const TcParams& p, int item, int& kb0, int& kb1) {
+  kb0 = 0; kb1 = p.nkb;
+  if (MODE == MODE_GEMM && p.splits > 1) {
+    const int per = p.m_tiles * p.n_tiles;
+    const int nbatch = p.n_items / per / p.splits;
+    const int sp = (item / per) / nbatch;
+    kb0 = sp * p.nkb_split;
+    kb1 = min(p.nkb, kb0 + p.nkb_split);
   }
 }
 
@@ -212,9 +229,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int njt = tiles_in_item<MODE, BN>(p, item);
         for (int jt = 0; jt < njt; ++jt) {
-          int arow, brow;
+          int arow, brow, kb0, kb1;
           tile_rows<MODE, BN>(p, item, jt, arow, brow);
-          for (int kb = 0; kb < nkb; ++kb) {
+          item_krange<MODE>(p, item, kb0, kb1);
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -240,7 +258,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
-          for (int kb = 0; kb < nkb; ++kb) {
+          int kb0, kb1;
+          item_krange<MODE>(p, item, kb0, kb1);
+          for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -253,7 +273,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // advance 32 bytes inside the swizzle atom
               // small cross terms first, dominant term last
-              umma_f16(d_tmem, dal + koff, dbh + koff, idesc, (kb | k) != 0);
+              umma_f16(d_tmem, dal + koff, dbh + koff, idesc, (kb != kb0) || (k != 0));
               umma_f16(d_tmem, dah + koff, dbl + koff, idesc, 1);
               umma_f16(d_tmem, dah + koff, dbh + koff, idesc, 1);
             }
@@ -323,15 +343,17 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       const float inv = p.a_scal[1] * p.b_scal[1];
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
         const int per = p.m_tiles * p.n_tiles;
-        const int b = item / per, rem = item - b * per;
+        const int bb = item / per, rem = item - bb * per;
+        const int nbatch = p.splits > 0 ? (p.n_items / per / p.splits) : (p.n_items / per);
+        const int b = bb % nbatch, sp = bb / nbatch;
         const int it = rem / p.n_tiles, jn = rem - it * p.n_tiles;
         const int row = it * kBM + q * 32 + lane;
         const uint32_t buf = tile & 1, use = tile >> 1;
         mbar_wait(&tmem_full[buf], use & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + lane_base + buf * BN;
-        float ssq = 0.f;
-        float* crow = p.C ? p.C + (long long)b * p.c_batch_stride + (long long)row * p.ldc : nullptr;
+        float ssq = 0.f, amax = 0.f;
+        float* crow = p.C ? p.C + (long long)sp * p.c_split_stride + (long long)b * p.c_batch_stride + (long long)row * p.ldc : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
           float v[32];
@@ -340,7 +362,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           if (row < p.m_valid && col0 < p.n_valid) {
             if (col0 + 32 <= p.n_valid) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) { v[i] *= inv; ssq = fmaf(v[i], v[i], ssq); }
+              for (int i = 0; i < 32; ++i) { v[i] *= inv; ssq = fmaf(v[i], v[i], ssq); amax = fmaxf(amax, fabsf(v[i])); }
               if (crow) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4)
@@ -352,6 +374,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
                 if (col0 + i < p.n_valid) {
                   const float x = v[i] * inv;
                   ssq = fmaf(x, x, ssq);
+                  amax = fmaxf(amax, fabsf(x));
                   if (crow) crow[col0 + i] = x;
                 }
             }
@@ -363,6 +386,11 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xffffffffu, ssq, o);
           if (lane == 0) atomicAdd(p.sq_out, (double)ssq);
+        }
+        if (p.absmax_out) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+          if (lane == 0) atomicMax(reinterpret_cast<int*>(p.absmax_out), __float_as_int(amax));
         }
       }
     }
@@ -464,7 +492,12 @@ int tc_gemm(const TcGemm& g, cudaStream_t st) {
   memset(&p, 0, sizeof(p));
   p.nkb = g.k_pad / kBK;
   p.m_tiles = ceil_div(g.m_pad, kBM); p.n_tiles = g.n_pad / BN;   // a 128-row box may run past a batch / the tensor: extra rows are discarded
-  p.n_items = g.batch * p.m_tiles * p.n_tiles;
+  p.splits = g.splits > 1 ? g.splits : 1;
+  p.nkb_split = ceil_div(p.nkb, p.splits);
+  p.splits = ceil_div(p.nkb, p.nkb_split);          // drop empty splits
+  p.c_split_stride = g.c_split_stride;
+  p.absmax_out = g.absmax_out;
+  p.n_items = p.splits * g.batch * p.m_tiles * p.n_tiles;
   p.a_batch_rows = g.a_batch_rows; p.b_batch_rows = g.b_batch_rows;
   p.m_valid = g.m; p.n_valid = g.n;
   p.a_scal = g.a_scal; p.b_scal = g.b_scal;
@@ -536,6 +569,7 @@ __global__ void scales_from_max_kernel(const float* __restrict__ mx, int first, 
     scal[2 * i + 1] = 1.f / s;
   }
 }
+__global__ void set_pair_kernel(float sc, float* __restrict__ scal2) { scal2[0] = sc; scal2[1] = 1.f / sc; }
 __global__ void set_scale_kernel(float bound, float* __restrict__ scal2) {
   int e = 0;
   frexpf(bound, &e);
@@ -619,6 +653,37 @@ __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, cons
   }
 }
 
+// QB planes [Mp, Jp]: row m = [2 Q_0[m,:] | 2 Q_1[m,:] | ... | 2 Q_R[m,:] | beta[m, 0..R) | 0...], Q_0 = Kuu^-1 (float64),
+// Q_r (float32, symmetric).  One common scale from mx2 = {max|Q| , max|beta|}; thread 0 publishes {scale, 1/scale}.
+__global__ void pack_qb_f16_kernel(const double* __restrict__ Kinv, const float* __restrict__ Qr, const double* __restrict__ beta,
+                                   int M, int Mp, int R, const float* __restrict__ mx2, float* __restrict__ scal2,
+                                   __half* __restrict__ QBh, __half* __restrict__ QBl) {
+  const float mmax = fmaxf(2.f * mx2[0], mx2[1]);
+  int ex = 0;
+  if (mmax > 0.f && isfinite(mmax)) frexpf(mmax, &ex);
+  const double sc = (double)ldexpf(1.f, 14 - ex);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scal2[0] = (float)sc; scal2[1] = (float)(1.0 / sc); }
+  const long long Jp = (long long)(R + 1) * Mp + 64;
+  const long long total = (long long)Mp * Jp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long j = e % Jp;
+    const int m = (int)(e / Jp);
+    double v = 0.0;
+    if (m < M) {
+      if (j < (long long)(R + 1) * Mp) {
+        const int blk = (int)(j / Mp), mm = (int)(j % Mp);
+        if (mm < M) v = 2.0 * sc * (blk == 0 ? Kinv[(long long)m * M + mm] : (double)Qr[((long long)(blk - 1) * Mp + m) * Mp + mm]);
+      } else {
+        const int r = (int)(j - (long long)(R + 1) * Mp);
+        if (r < R) v = sc * beta[(long long)m * R + r];
+      }
+    }
+    const __half hi = __float2half_rn((float)v);
+    QBh[e] = hi;
+    QBl[e] = __float2half_rn((float)(v - (double)__half2float(hi)));
+  }
+}
+
 __global__ void split_rows_kernel(const float* __restrict__ Kt, long long T, int Mp, long long Tpad, const float* __restrict__ kscal,
                                   __half* __restrict__ Kh, __half* __restrict__ Kl) {
   const float s = kscal[0];
@@ -664,6 +729,16 @@ void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   t.Lph = c.take((size_t)Mp * Mp * 2);
   t.Lpl = c.take((size_t)Mp * Mp * 2);
   t.Wr32 = (float*)c.take((size_t)R * Mp * Mp * 4);
+  t.BRh = c.take((size_t)R * Mp * Mp * 2);
+  t.BRl = c.take((size_t)R * Mp * Mp * 2);
+  t.Br32 = (float*)c.take((size_t)R * Mp * Mp * 4);
+  {
+    const size_t Jp = (size_t)(R + 1) * Mp + 64;
+    t.QBh = c.take((size_t)Mp * Jp * 2);
+    t.QBl = c.take((size_t)Mp * Jp * 2);
+  }
+  t.ZTh = c.take((size_t)t.Lp * Mp * 2);
+  t.ZTl = c.take((size_t)t.Lp * Mp * 2);
   t.Wmh = t.Wml = nullptr;
   t.bytes = align_up(c.off, 1024);
 }
@@ -687,7 +762,8 @@ int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double*
 //   trace = sum_r |Lp^-1 L_r|_F^2   (GPflow gauss_kl / DS/layers.py:250)                  -> *trace_out (double)
 // Linv/G/Lpinv/beta are float64 (Cholesky-quality); only these products run split-fp16 on tcgen05.
 int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
-                      const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out, cudaStream_t st) {
+                      const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out,
+                      const double* Kinv, cudaStream_t st) {
   const int M = t.M, Mp = t.Mp, R = t.R;
   int rc;
   cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
@@ -728,7 +804,45 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
   scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
   pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
                                                    (__half*)t.Wh, (__half*)t.Wl);
-  return check_launch("tc_build_operands", 2);
+  if ((rc = check_launch("tc_build_operands", 2))) return rc;
+  if (!Kinv) return DCGP_OK;
+  // ---- backward operands: B_r = G L_r (= W_r^T), Q_r = B_r B_r^T, QB planes [Mp, Jp] = [2Q_0 | ... | 2Q_R | beta | 0]
+  {
+    TcGemm b1;
+    memset(&b1, 0, sizeof(b1));
+    b1.Ah = t.Gh; b1.Al = t.Gl; b1.a_rows_total = Mp; b1.a_batch_rows = 0;
+    b1.Bh = t.QTh; b1.Bl = t.QTl; b1.b_rows_total = (long long)R * Mp; b1.b_batch_rows = Mp;
+    b1.batch = R; b1.m = M; b1.n = M; b1.m_pad = Mp; b1.n_pad = Mp; b1.k_pad = Mp;
+    b1.a_scal = t.scal + 6; b1.b_scal = t.scal + 4;
+    b1.C = t.Br32; b1.c_batch_stride = (long long)Mp * Mp; b1.ldc = Mp;
+    if (M != Mp) cudaMemsetAsync(t.Br32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
+    if ((rc = tc_gemm(b1, st))) return rc;
+    if ((rc = maxabs_f32(t.Br32, (long long)R * Mp * Mp, t.mx + 7, st))) return rc;
+    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 7, 1, t.scal);
+    split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(t.Br32, (long long)R * Mp, Mp, (long long)R * Mp, t.scal + 14, (__half*)t.BRh,
+                                                     (__half*)t.BRl);
+    TcGemm b2;
+    memset(&b2, 0, sizeof(b2));
+    b2.Ah = t.BRh; b2.Al = t.BRl; b2.a_rows_total = (long long)R * Mp; b2.a_batch_rows = Mp;
+    b2.Bh = t.BRh; b2.Bl = t.BRl; b2.b_rows_total = (long long)R * Mp; b2.b_batch_rows = Mp;
+    b2.batch = R; b2.m = M; b2.n = M; b2.m_pad = Mp; b2.n_pad = Mp; b2.k_pad = Mp;
+    b2.a_scal = t.scal + 14; b2.b_scal = t.scal + 14;
+    b2.C = t.Br32; b2.c_batch_stride = (long long)Mp * Mp; b2.ldc = Mp;     // Br32 now holds Q_r
+    if ((rc = tc_gemm(b2, st))) return rc;
+    if ((rc = maxabs_f32(t.Br32, (long long)R * Mp * Mp, t.mx + 5, st))) return rc;
+    if ((rc = maxabs_f64(Kinv, M, M, M, 0, t.mx + 5, st))) return rc;
+    if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 6, st))) return rc;
+    pack_qb_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Kinv, t.Br32, beta, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl);
+    if ((rc = check_launch("tc_build_backward_operands", 3))) return rc;
+  }
+  return DCGP_OK;
+}
+
+int tc_gemm_splits(const TcGemm& g) {
+  const int nkb = g.k_pad / kBK;
+  const int sp = g.splits > 1 ? g.splits : 1;
+  const int per = ceil_div(nkb, sp);
+  return ceil_div(nkb, per);
 }
 
 // ============================================================================================ K-A: Kuf on tensor cores
@@ -943,9 +1057,14 @@ __global__ void pack_z_f16_kernel(const double* __restrict__ Z, int M, int Mp, i
   if (threadIdx.x == 0) zz[m] = (float)(sh[0] + sh[1] + sh[2] + sh[3]);
 }
 
+__global__ void pack_zt_f16_kernel(const double* __restrict__ Z, int M, int Mp, int L, int Lp, double inv_ls,
+                                   __half* __restrict__ ZTh, __half* __restrict__ ZTl);   // dcgp_tc_bwd.inc
+
 int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st) {
   pack_z_f16_kernel<<<t.Mp, 128, 0, st>>>(Z, M, t.Mp, L, t.Lp, inv_ls, (__half*)t.Zh, (__half*)t.Zl, t.zz);
-  return check_launch("pack_z_f16");
+  pack_zt_f16_kernel<<<grid_for((long long)t.Lp * t.Mp, 2048), 256, 0, st>>>(Z, M, t.Mp, L, t.Lp, inv_ls, (__half*)t.ZTh, (__half*)t.ZTl);
+  set_pair_kernel<<<1, 1, 0, st>>>(kXScale, t.scal + 12);
+  return check_launch("pack_z_f16", 3);
 }
 
 template <int BN>
@@ -1055,5 +1174,7 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
   if ((rc = tc_split_rows(Kzx, n_rows, Mp, a.kz, st))) return rc;
   return tc_cond(prep, a.kz, n_rows, Mp, R, acc, mean_t, st);
 }
+
+#include "dcgp_tc_bwd.inc"
 
 }  // namespace dcgp

@@ -19,13 +19,19 @@ struct TcPrep {
   void *Gh, *Gl;     // [Mp, Mp]
   void *Lph, *Lpl;   // [Mp, Mp]
   float* Wr32;       // [R*Mp, Mp] fp32 W_r (tensor-core product)
+  // ---- operands of the backward pass
+  void *BRh, *BRl;   // [R*Mp, Mp]   B_r = W_r^T = G L_r
+  float* Br32;       // [R*Mp, Mp]   (also reused for Q_r = B_r B_r^T)
+  void *QBh, *QBl;   // [Mp, Jp]     rows m: [2 Q_0[m,:] | ... | 2 Q_R[m,:] | beta[m,:] | 0], Jp = (R+1)*Mp + 64
+  void *ZTh, *ZTl;   // [Lp, Mp]     (Z / lengthscale)^T * kXScale
   size_t bytes;
 };
 void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf);
 int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double* Wr, const double* beta, int M, int Mp,
                      int R, cudaStream_t st);
 int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
-                      const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out, cudaStream_t st);
+                      const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out,
+                      const double* Kinv, cudaStream_t st);
 int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st);
 
 struct TcCondWork {
@@ -49,7 +55,10 @@ struct TcGemm {
   const float *a_scal, *b_scal;   // device {scale, 1/scale}
   float* C; long long c_batch_stride; int ldc;   // optional fp32 output (unscaled values)
   double* sq_out;                                // optional: += sum of squares of C
+  float* absmax_out;                             // optional: atomic max |C| (zero it first)
+  int splits; long long c_split_stride;          // split-K: partial C per split (caller reduces); splits <= 1 = off
 };
+int tc_gemm_splits(const TcGemm& g);             // number of splits tc_gemm will really use
 int tc_gemm(const TcGemm& g, cudaStream_t st);
 
 struct TcApplyWork {
@@ -63,5 +72,19 @@ void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_
 int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const float* zs,
                    float* Kt32, const double* patch_weights, const float* X, int n_rows, float* Kzx, float* acc,
                    float* mean_t, cudaStream_t st);
+
+// Workspace of the backward pass of one layer (see dcgp_tc_bwd.inc)
+struct TcBwdWork {
+  int Jp, Lp, splits2, splits4;
+  size_t Tpad, Tkpad;
+  float *gm, *s, *gknn, *scal, *dK32, *part2, *rowsum, *rowdot, *DDZ, *part4;
+  double *colsum, *DDX;
+  void *KSh, *KSl, *KSTh, *KSTl, *KTh, *KTl, *Dh, *Dl, *DTh, *DTl, *PTh, *PTl;
+  size_t bytes;
+};
+void tc_carve_bwd(TcBwdWork& b, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, int P, void* buf);
+int tc_layer_backward(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const TcBwdWork& b,
+                      const double* Z, const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
+                      const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, cudaStream_t st);
 
 }  // namespace dcgp

@@ -70,7 +70,7 @@ class DGP_Base(object):
         idx = self._mb.next_indices()
         return self.X_all[idx], self.Y_all[idx]
 
-    def _build_likelihood(self, X=None, Y=None, zs=None, n_global=None):
+    def _build_likelihood(self, X=None, Y=None, zs=None, n_global=None, keep=False):
         """DS/dgp.py:92-98: ELBO = sum_n E_q[log p(y_n|f_n)] * num_data/batch - sum_l KL_l, as a device scalar.
         The whole step stays on the stream; nothing is read back here."""
         if X is None:
@@ -92,7 +92,9 @@ class DGP_Base(object):
                 layer._ready.record(side)
             layer._hold = True
         try:
-            Fmean, Fvar = self._build_predict(X, full_cov=False, S=S, zs=zs)
+            Fs, Fmeans, Fvars = self.propagate(X, full_cov=False, S=S, zs=zs)
+            Fmean, Fvar = Fmeans[-1], Fvars[-1]
+            self._fwd = (Fs, Fmeans, Fvars) if keep else None     # the backward pass re-uses the layer outputs
             K = Fmean.shape[2]
             lik = self.likelihood.likelihood
             lik.variational_expectations(Fmean.reshape(S * N, K), Fvar.reshape(S * N, K), Y, S=S, out_sum=self._sum)

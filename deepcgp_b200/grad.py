@@ -1,0 +1,249 @@
+"""ELBO gradient and optimiser step: the reference gets gradients from TensorFlow autodiff inside
+GPflow's AdamOptimizer (conv_gp/experiment.py:84-108); here the minibatch-sized backward runs in libdcgp.so
+(dcgp_layer_backward: four split-fp16 tcgen05 GEMMs per layer + elementwise kernels) and the small minibatch-independent
+chain rule (Q_blk, beta, KL -> Z, kernel hyper-parameters, q_mu, q_sqrt) is dense float64 algebra on the device.
+
+NOTE (round 1): that M-only chain rule is evaluated with torch.autograd over torch.linalg ops (cuSOLVER/cuBLAS, float64);
+it is O(R M^3), independent of the batch, and is the one place on the step where library kernels are used.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .dist import allreduce_sum_, world
+from .kernels import JITTER
+from .layers import ConvLayer
+
+
+def _rbf(Z, variance, lengthscale):
+    Zs = Z / lengthscale
+    n = (Zs * Zs).sum(1)
+    d = n[:, None] + n[None, :] - 2.0 * Zs @ Zs.T
+    return variance * torch.exp(-0.5 * d)
+
+
+def softplus_inv(x):
+    """GPflow transforms.positive: x = log(1 + exp(u)) + 1e-6"""
+    y = x - 1e-6
+    return y + math.log(-math.expm1(-y))
+
+
+class LayerBackward(object):
+    """Per-layer buffers + the M-only chain rule."""
+
+    def __init__(self, layer):
+        self.layer = layer
+        d = layer._desc()
+        self.M, self.R = layer.num_inducing, layer._R
+        self.Mp = (self.M + 63) // 64 * 64
+        self.Jp = (self.R + 1) * self.Mp + 64
+        dev = layer.device
+        self.L = layer._view.patch_length
+        self.gQB = torch.zeros((self.Jp, self.Mp), dtype=torch.float64, device=dev)
+        self.gZ = torch.zeros((self.M, self.L), dtype=torch.float64, device=dev)
+        self.gscal = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.gw = torch.zeros(layer._view.patch_count, dtype=torch.float64, device=dev)
+        self.ws = _lib.Workspace()
+
+    def t_sized(self, X, n_rep, g_mean, g_var, need_gX):
+        """dcgp_layer_backward -> gX (or None); fills gQB, gZ, gscal, gw."""
+        layer = self.layer
+        d = layer._desc()
+        X = _lib.f32(X, layer.device)
+        n_rows = X.shape[0]
+        gX = torch.empty_like(X) if need_gX else None
+        ws = self.ws.get("bwd", _lib.lib.dcgp_backward_workspace_bytes(d, n_rows, n_rep), layer.device)
+        aws = layer._ws.get("apply", 0, layer.device)
+        w = layer._patch_weights()
+        self._keep = (X, g_mean, g_var, w)
+        _lib.check(_lib.lib.dcgp_layer_backward(
+            d, _lib.ptr(layer._prep), _lib.ptr(aws), _lib.ptr(layer._keep[0]), _lib.ptr(w), _lib.ptr(X), n_rows, n_rep,
+            _lib.ptr(g_mean), _lib.ptr(g_var), _lib.ptr(gX), _lib.ptr(self.gQB), _lib.ptr(self.gZ), _lib.ptr(self.gscal),
+            _lib.ptr(self.gw) if layer._kind == _lib.LAYER_SVGP_CONV else None, _lib.ptr(ws), ws.numel(), _lib.stream()))
+        return gX
+
+    def m_only(self, kl_weight=1.0):
+        """Chain rule through the minibatch-independent operands; returns d ELBO / d{Z, variance, lengthscale, q_mu,
+        q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that summing over ranks counts the KL once."""
+        layer = self.layer
+        dev = layer.device
+        M, R, Mp = self.M, self.R, self.Mp
+        gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
+        gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
+        with torch.enable_grad():
+            Z = layer.feature.Z.detach().to(torch.float64).clone().requires_grad_(True)
+            var = torch.tensor(float(layer._base_kernel.variance), dtype=torch.float64, device=dev, requires_grad=True)
+            ls = torch.tensor(float(layer._base_kernel.lengthscales), dtype=torch.float64, device=dev, requires_grad=True)
+            q_mu = layer.q_mu.detach().clone().requires_grad_(True)
+            q_sqrt = layer.q_sqrt.detach().clone().requires_grad_(True)
+            eye = torch.eye(M, dtype=torch.float64, device=dev)
+            Kuu = _rbf(Z, var, ls) + JITTER * eye
+            Lm = torch.linalg.cholesky(Kuu)
+            Linv = torch.linalg.solve_triangular(Lm, eye, upper=False)
+            Kinv = Linv.T @ Linv
+            Lq = torch.tril(q_sqrt)
+            if layer.white:
+                B = Linv.T @ Lq
+                beta = Linv.T @ q_mu
+            else:
+                B = Kinv @ Lq
+                beta = Kinv @ q_mu
+            Qr = B @ B.transpose(1, 2)
+            obj = (gQ[0] * Kinv).sum() + (gQ[1:] * Qr).sum() + (gbeta * beta).sum()
+            # KL (layers.py:137-147 / DS/layers.py:231-256)
+            logdet_q = torch.log(torch.diagonal(Lq, dim1=1, dim2=2) ** 2).sum()
+            if layer.white:
+                kl = 0.5 * ((q_mu ** 2).sum() - M * R - logdet_q + (Lq ** 2).sum())
+            else:
+                if isinstance(layer, ConvLayer):
+                    Lp = torch.linalg.cholesky(_rbf(layer.Z_prior.to(torch.float64), var, ls) + JITTER * eye)
+                else:
+                    Lp = Lm
+                a = torch.linalg.solve_triangular(Lp, q_mu, upper=False)
+                LpiLq = torch.linalg.solve_triangular(Lp, Lq, upper=False)
+                kl = 0.5 * ((a ** 2).sum() - M * R - logdet_q + (LpiLq ** 2).sum() + R * torch.log(torch.diagonal(Lp) ** 2).sum())
+            obj = obj - kl_weight * kl
+            gZ, gvar, gls, gq_mu, gq_sqrt = torch.autograd.grad(obj, [Z, var, ls, q_mu, q_sqrt])
+        out = {"Z": gZ + self.gZ, "variance": gvar + self.gscal[0], "lengthscale": gls + self.gscal[1], "q_mu": gq_mu,
+               "q_sqrt": torch.tril(gq_sqrt)}
+        if layer._kind == _lib.LAYER_SVGP_CONV:
+            out["patch_weights"] = self.gw.clone()
+        return out
+
+
+class ElboGradient(object):
+    """elbo, grads = ElboGradient(model)(X, Y, zs): forward ELBO + its gradient w.r.t. every layer's parameters."""
+
+    def __init__(self, model):
+        self.model = model
+        self.bwd = [LayerBackward(l) for l in model.layers]
+
+    def __call__(self, X, Y, zs=None, n_global=None):
+        model = self.model
+        X = _lib.f32(X, model.device)
+        N, S = X.shape[0], model.num_samples
+        if zs is None:
+            zs = [torch.randn((S, N, l.num_outputs), dtype=torch.float32, device=model.device) for l in model.layers]
+        zs = [_lib.f32(z, model.device) for z in zs]
+        elbo = model._build_likelihood(X, Y, zs=zs, n_global=n_global, keep=True)
+        Fs, Fmeans, Fvars = model._fwd
+        rank, wsize = world()
+        K = Fmeans[-1].shape[2]
+        coef = float(model.num_data) / float(n_global or N) / S
+        Yd = torch.as_tensor(Y, device=model.device).reshape(-1).to(torch.int32).contiguous()
+        Fm, Fv = Fmeans[-1].reshape(S * N, K).contiguous(), Fvars[-1].reshape(S * N, K).contiguous()
+        g_mean, g_var = torch.empty_like(Fm), torch.empty_like(Fv)
+        lik = model.likelihood.likelihood
+        _lib.check(_lib.lib.dcgp_multiclass_varexp_grad(_lib.ptr(Fm), _lib.ptr(Fv), _lib.ptr(Yd), S, N, K, lik.epsilon, coef,
+                                                        _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
+        grads = [None] * len(model.layers)
+        for i in range(len(model.layers) - 1, -1, -1):
+            first = (i == 0)
+            Xin = X if first else Fs[i - 1].reshape(S * N, -1)
+            gX = self.bwd[i].t_sized(Xin, S if first else 1, g_mean, g_var, need_gX=not first)
+            grads[i] = self.bwd[i].m_only(kl_weight=1.0 / wsize)
+            if not first:
+                n = gX.numel()
+                g_mean, g_var = torch.empty_like(gX), torch.empty_like(gX)
+                zprev = zs[i - 1].reshape(-1).contiguous()
+                vprev = Fvars[i - 1].reshape(-1).contiguous()
+                _lib.check(_lib.lib.dcgp_sample_backward(_lib.ptr(gX), _lib.ptr(zprev), _lib.ptr(vprev), n, JITTER,
+                                                         _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
+        return elbo, grads
+
+
+class Adam(object):
+    """tf.train.AdamOptimizer on GPflow's unconstrained variables (experiment.py:97-99): Z, softplus^-1(variance),
+    softplus^-1(lengthscale), q_mu, the lower triangle of q_sqrt, patch_weights -- all layers in ONE flat float64 vector
+    (one fused kernel; one all-reduce of the flat gradient when image-sharded)."""
+
+    NAMES = ("Z", "variance", "lengthscale", "q_mu", "q_sqrt", "patch_weights")
+
+    def __init__(self, model, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.model, self.lr, self.b1, self.b2, self.eps = model, lr, beta1, beta2, eps
+        self.step_no = 0
+        dev = model.device
+        self.slots = []
+        off = 0
+        for li, layer in enumerate(model.layers):
+            shapes = {"Z": tuple(layer.feature.Z.shape), "variance": (1,), "lengthscale": (1,), "q_mu": tuple(layer.q_mu.shape),
+                      "q_sqrt": tuple(layer.q_sqrt.shape)}
+            if layer._kind == _lib.LAYER_SVGP_CONV:
+                shapes["patch_weights"] = (layer._view.patch_count,)
+            for name in self.NAMES:
+                if name in shapes:
+                    n = int(np.prod(shapes[name]))
+                    self.slots.append((li, name, off, n, shapes[name]))
+                    off += n
+        self.n = off
+        self.flat = torch.zeros(off, dtype=torch.float64, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float64, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float64, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float64, device=dev)
+        self._pull()
+
+    def _view(self, buf, slot):
+        _, _, off, n, shape = slot
+        return buf[off:off + n].view(shape)
+
+    def _pull(self):
+        for slot in self.slots:
+            li, name = slot[0], slot[1]
+            layer = self.model.layers[li]
+            dst = self._view(self.flat, slot)
+            if name == "Z":
+                dst.copy_(layer.feature.Z)
+            elif name == "variance":
+                dst.fill_(softplus_inv(float(layer._base_kernel.variance)))
+            elif name == "lengthscale":
+                dst.fill_(softplus_inv(float(layer._base_kernel.lengthscales)))
+            elif name == "q_mu":
+                dst.copy_(layer.q_mu)
+            elif name == "q_sqrt":
+                dst.copy_(layer.q_sqrt)
+            else:
+                dst.copy_(_lib.f64(layer.kern.patch_weights, self.flat.device))
+
+    def _push(self):
+        hyp = []
+        for slot in self.slots:
+            li, name = slot[0], slot[1]
+            layer = self.model.layers[li]
+            src = self._view(self.flat, slot)
+            if name == "Z":
+                layer.feature.Z = src
+            elif name in ("variance", "lengthscale"):
+                hyp.append((layer, name, src))
+            elif name == "q_mu":
+                layer.q_mu = src
+            elif name == "q_sqrt":
+                layer.q_sqrt = src
+            else:
+                layer.kern.patch_weights = src
+        # kernel hyper-parameters travel by value in dcgp_layer_desc: ONE host read-back per step for all layers
+        vals = torch.nn.functional.softplus(torch.cat([s for _, _, s in hyp])) + 1e-6
+        vals = vals.cpu().tolist()
+        for (layer, name, _), v in zip(hyp, vals):
+            if name == "variance":
+                layer._base_kernel.variance = v
+            else:
+                layer._base_kernel.lengthscales = v
+
+    def step(self, grads):
+        """grads: list (per layer) of dicts of d ELBO / d constrained parameter (this rank's share)."""
+        for slot in self.slots:
+            li, name = slot[0], slot[1]
+            g = grads[li][name]
+            dst = self._view(self.grad, slot)
+            if name in ("variance", "lengthscale"):
+                u = self._view(self.flat, slot)
+                dst.copy_((g * torch.sigmoid(u)).reshape(1))          # d softplus(u) / du
+            else:
+                dst.copy_(g.reshape(dst.shape))
+        allreduce_sum_(self.grad)                                       # the single exchange of the image-sharded step
+        self.step_no += 1
+        _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v), self.n,
+                                      self.lr, self.b1, self.b2, self.eps, self.step_no, 1, _lib.stream()))
+        self._push()

@@ -123,6 +123,34 @@ int dcgp_layer_apply(const dcgp_layer_desc* d, const void* prep, const double* p
                      int n_rows, int n_rep, const float* z, int algo, float* mean, float* var, float* sample,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* ---- backward pass (the reference gets these from TensorFlow autodiff inside GPflow's AdamOptimizer,
+ * experiment.py:84-108).  Tensor-core path only.
+ *
+ * dcgp_layer_backward: gradient of the objective through the minibatch-sized part of one layer.
+ *   prep, apply_ws : the buffers the matching dcgp_layer_prepare / dcgp_layer_apply (algo = DCGP_ALGO_TC) calls used
+ *                    (the forward leaves the kernel-matrix planes in apply_ws).
+ *   g_mean, g_var  : [n_rows*n_rep, D] float32 gradients w.r.t. the layer's mean / var outputs.
+ *   gX   [n_rows, H*W*C] float32, or NULL when the input needs no gradient (first layer)
+ *   gQB  [(R+1)*Mp + 64, Mp] float64, Mp = M rounded up to 64: rows blk*Mp + i hold dQ_blk[i, :] where
+ *        acc_blk(t) = k_t^T Q_blk k_t (Q_0 = Kuu^-1, Q_r = G L_r L_r^T G^T), rows (R+1)*Mp + r hold dbeta[:, r]
+ *   gZ   [M, L] float64: direct path through Kuf;   gscal[4]: {d/dvariance, d/dlengthscale, -, -} direct paths
+ *   gw   [P] float64 (SVGP_CONV only).  The M-only chain rule (Q, beta, KL -> Z, hyper-parameters, q_mu, q_sqrt) is
+ *        small dense float64 algebra done by the host (deepcgp_b200/grad.py). */
+size_t dcgp_backward_workspace_bytes(const dcgp_layer_desc* d, int n_rows, int n_rep);
+int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep, const void* apply_ws, const double* Z,
+                        const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
+                        const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, void* ws,
+                        size_t ws_bytes, void* stream);
+/* gradient of coef * sum(varexp) w.r.t. Fmu, Fvar ([S*N, K] float32) */
+int dcgp_multiclass_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K,
+                                double epsilon, double coef, float* gmu, float* gvar, void* stream);
+/* DS/utils.py:41 backward: g_mean = gF, g_var = gF * z / (2 sqrt(var + jitter)) */
+int dcgp_sample_backward(const float* gF, const float* z, const float* var, size_t n, double jitter, float* g_mean,
+                         float* g_var, void* stream);
+/* Adam on a flat float64 vector (experiment.py:97-99; tf.train.AdamOptimizer update rule); maximize != 0 ascends */
+int dcgp_adam(double* param, const double* grad, double* m, double* v, size_t n, double lr, double beta1, double beta2,
+              double eps, int step, int maximize, void* stream);
+
 /* kernels.py:117-133 ConvKernel.Kzx -> out[M,N] f32; kernels.py:106-115 ConvKernel.Kdiag -> out[N] f32. */
 size_t dcgp_convkernel_kzx_workspace_bytes(const dcgp_layer_desc* d, int N);
 int dcgp_convkernel_kzx(const dcgp_layer_desc* d, const double* Z, const double* patch_weights, const float* X,
