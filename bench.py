@@ -219,13 +219,25 @@ def run_ours(args, cfg):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
     elbo_host = torch.empty(1, dtype=torch.float64).pin_memory()
 
+    import deepcgp_b200 as D
+    eg = D.ElboGradient(model)
+    opt = D.Adam(model, lr=args.lr)
+
+    def elbo_step(x, y):
+        """One optimisation step: forward ELBO, backward, (all-reduce of the flat gradient), Adam update."""
+        if args.forward_only:
+            return model._build_likelihood(x, y, zs=zs, n_global=n_global)
+        e, grads = eg(x, y, zs=zs, n_global=n_global)
+        opt.step(grads)
+        return e
+
     def step_resident(i):
-        return model._build_likelihood(devX[i % n_batches], devY[i % n_batches], zs=zs, n_global=n_global)
+        return elbo_step(devX[i % n_batches], devY[i % n_batches])
 
     def step_e2e(i):
         x = hostX[i % n_batches].to(device, non_blocking=True)
         y = hostY[i % n_batches].to(device, non_blocking=True)
-        e = model._build_likelihood(x, y, zs=zs, n_global=n_global)
+        e = elbo_step(x, y)
         elbo_host.copy_(e.reshape(1), non_blocking=True)
         return e
 
@@ -278,10 +290,13 @@ def run_ours(args, cfg):
                "sample": "%d images x S=%d, full 3-layer forward ELBO in %.1f s, float64 NumPy/SciPy oracle port "
                          "(reference TF/GPflow path not installable)" % (args.ref_images, S, dt)}
     total_flops, _ = algorithmic_flops(cfg, B)
+    if not args.forward_only:
+        total_flops *= 3.0      # SURVEY 8d convention: backward = 2x forward
     line = {"metric": "ELBO-step images/sec", "value": n_global / (ms_res * 1e-3), "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp16x2-split tensor cores (fp32 accumulate) + f64 M-only", "data": "synthetic",
-            "config": {"workload": args.config + ": " + cfg["desc"], "step": "forward ELBO (a1-a9); backward+Adam not built yet",
+            "config": {"workload": args.config + ": " + cfg["desc"], "step": "forward ELBO only" if args.forward_only else
+                       "forward ELBO + backward + gradient all-reduce + Adam (all trainables)",
                        "images_per_gpu": B, "num_samples": S, "l2_flush": "256 MiB buffer written between timed steps",
                        "algorithmic_gflop_per_step_per_gpu": total_flops / 1e9, "elbo": elbo_val},
             "e2e": {"value": n_global / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
@@ -347,6 +362,8 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--ref-images", type=int, default=32, help="images in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--forward-only", action="store_true", help="time the forward ELBO alone (diagnostic)")
+    ap.add_argument("--lr", type=float, default=1e-3)
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -67,6 +67,80 @@ class LayerBackward(object):
     def m_only(self, kl_weight=1.0):
         """Chain rule through the minibatch-independent operands; returns d ELBO / d{Z, variance, lengthscale, q_mu,
         q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that summing over ranks counts the KL once."""
+        if self.layer.white:
+            return self._m_only_autograd(kl_weight)
+        return self._m_only_closed_form(kl_weight)
+
+    @staticmethod
+    def _rbf_parts(Z, var, ls):
+        Zs = Z / ls
+        n = (Zs * Zs).sum(1)
+        D = n[:, None] + n[None, :] - 2.0 * Zs @ Zs.T
+        return var * torch.exp(-0.5 * D), D
+
+    @staticmethod
+    def _rbf_chain(G, Kn, D, Z, var, ls, need_Z=True):
+        """Gradients of sum(G * K(Z)) for K = var * exp(-D/2): d/dvar, d/dls and (optionally) d/dZ."""
+        H = G * Kn
+        gvar = H.sum() / var
+        gls = (H * D).sum() / ls
+        if not need_Z:
+            return gvar, gls, None
+        Hs = H + H.T
+        gZ = -(Hs.sum(1, keepdim=True) * Z - Hs @ Z) / (ls * ls)
+        return gvar, gls, gZ
+
+    @torch.no_grad()
+    def _m_only_closed_form(self, kl_weight):
+        """Non-whitened case, written out as ~15 batched float64 GEMMs (no autograd graph, no triangular solves):
+             Q_0 = Kinv, Q_r = B_r B_r^T with B_r = Kinv L_r, beta = Kinv q_mu       (Kinv = Kuu^-1)
+             KL  = 1/2 [q_mu^T Kp^-1 q_mu - MR - sum log diag(L_r)^2 + sum <L_r, Kp^-1 L_r> + R log|Kp|]"""
+        layer = self.layer
+        dev = layer.device
+        M, R, Mp = self.M, self.R, self.Mp
+        gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
+        gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
+        Z = layer.feature.Z.to(torch.float64)
+        var, ls = float(layer._base_kernel.variance), float(layer._base_kernel.lengthscales)
+        q_mu, Lq = layer.q_mu, torch.tril(layer.q_sqrt)
+        eye = torch.eye(M, dtype=torch.float64, device=dev)
+        Kn, D = self._rbf_parts(Z, var, ls)
+        # cholesky_ex: no host-side error check (torch.linalg.cholesky synchronises to read `info`); the forward's own
+        # Cholesky already reports a non-PD Kuu through the layer's device-side info flag
+        Kinv = torch.cholesky_inverse(torch.linalg.cholesky_ex(Kn + JITTER * eye, check_errors=False)[0])
+        B = Kinv @ Lq                                                    # [R,M,M]
+        U = (gQ[1:] + gQ[1:].transpose(1, 2)) @ B                        # d/dB_r
+        gLq = Kinv @ U                                                   # d/dL_r (through B_r)
+        GK = gQ[0] + torch.einsum("rij,rkj->ik", U, Lq) + gbeta @ q_mu.T # d/dKinv
+        g_qmu = Kinv @ gbeta
+        GU = -(Kinv @ GK @ Kinv)                                         # d/dKuu
+        conv = isinstance(layer, ConvLayer)
+        if conv:    # prior = Kuu at the initial Z (a constant) with the live hyper-parameters (layers.py:149-150)
+            Zp = layer.Z_prior.to(torch.float64)
+            Kpn, Dp = self._rbf_parts(Zp, var, ls)
+            Kpinv = torch.cholesky_inverse(torch.linalg.cholesky_ex(Kpn + JITTER * eye, check_errors=False)[0])
+            C = Kpinv @ Lq
+            a = Kpinv @ q_mu
+        else:
+            Kpinv, C, a = Kinv, B, g_qmu.new_empty(0)
+            a = Kinv @ q_mu
+        dKL_dKp = 0.5 * (-(a @ a.T) - torch.einsum("rij,rkj->ik", C, C) + R * Kpinv)
+        g_qmu = g_qmu - kl_weight * a
+        gLq = gLq - kl_weight * (C - torch.diag_embed(1.0 / torch.diagonal(Lq, dim1=1, dim2=2)))
+        if conv:
+            gvar_p, gls_p, _ = self._rbf_chain(-kl_weight * dKL_dKp, Kpn, Dp, Zp, var, ls, need_Z=False)
+        else:
+            GU = GU - kl_weight * dKL_dKp
+            gvar_p = gls_p = 0.0
+        gvar, gls, gZ = self._rbf_chain(GU, Kn, D, Z, var, ls)
+        out = {"Z": gZ + self.gZ, "variance": gvar + gvar_p + self.gscal[0], "lengthscale": gls + gls_p + self.gscal[1],
+               "q_mu": g_qmu, "q_sqrt": torch.tril(gLq)}
+        if layer._kind == _lib.LAYER_SVGP_CONV:
+            out["patch_weights"] = self.gw.clone()
+        return out
+
+    def _m_only_autograd(self, kl_weight=1.0):
+        """Whitened case (non-default, arguments.py:33): torch.autograd over the same float64 algebra."""
         layer = self.layer
         dev = layer.device
         M, R, Mp = self.M, self.R, self.Mp
@@ -80,31 +154,15 @@ class LayerBackward(object):
             q_sqrt = layer.q_sqrt.detach().clone().requires_grad_(True)
             eye = torch.eye(M, dtype=torch.float64, device=dev)
             Kuu = _rbf(Z, var, ls) + JITTER * eye
+            Lq = torch.tril(q_sqrt)
+            logdet_q = torch.log(torch.diagonal(Lq, dim1=1, dim2=2) ** 2).sum()
             Lm = torch.linalg.cholesky(Kuu)
             Linv = torch.linalg.solve_triangular(Lm, eye, upper=False)
             Kinv = Linv.T @ Linv
-            Lq = torch.tril(q_sqrt)
-            if layer.white:
-                B = Linv.T @ Lq
-                beta = Linv.T @ q_mu
-            else:
-                B = Kinv @ Lq
-                beta = Kinv @ q_mu
-            Qr = B @ B.transpose(1, 2)
-            obj = (gQ[0] * Kinv).sum() + (gQ[1:] * Qr).sum() + (gbeta * beta).sum()
-            # KL (layers.py:137-147 / DS/layers.py:231-256)
-            logdet_q = torch.log(torch.diagonal(Lq, dim1=1, dim2=2) ** 2).sum()
-            if layer.white:
-                kl = 0.5 * ((q_mu ** 2).sum() - M * R - logdet_q + (Lq ** 2).sum())
-            else:
-                if isinstance(layer, ConvLayer):
-                    Lp = torch.linalg.cholesky(_rbf(layer.Z_prior.to(torch.float64), var, ls) + JITTER * eye)
-                else:
-                    Lp = Lm
-                a = torch.linalg.solve_triangular(Lp, q_mu, upper=False)
-                LpiLq = torch.linalg.solve_triangular(Lp, Lq, upper=False)
-                kl = 0.5 * ((a ** 2).sum() - M * R - logdet_q + (LpiLq ** 2).sum() + R * torch.log(torch.diagonal(Lp) ** 2).sum())
-            obj = obj - kl_weight * kl
+            B = Linv.T @ Lq
+            beta = Linv.T @ q_mu
+            kl = 0.5 * ((q_mu ** 2).sum() - M * R - logdet_q + (Lq ** 2).sum())
+            obj = (gQ[0] * Kinv).sum() + (gQ[1:] * (B @ B.transpose(1, 2))).sum() + (gbeta * beta).sum() - kl_weight * kl
             gZ, gvar, gls, gq_mu, gq_sqrt = torch.autograd.grad(obj, [Z, var, ls, q_mu, q_sqrt])
         out = {"Z": gZ + self.gZ, "variance": gvar + self.gscal[0], "lengthscale": gls + self.gscal[1], "q_mu": gq_mu,
                "q_sqrt": torch.tril(gq_sqrt)}
@@ -119,6 +177,7 @@ class ElboGradient(object):
     def __init__(self, model):
         self.model = model
         self.bwd = [LayerBackward(l) for l in model.layers]
+        self._side = None
 
     def __call__(self, X, Y, zs=None, n_global=None):
         model = self.model
@@ -139,11 +198,17 @@ class ElboGradient(object):
         _lib.check(_lib.lib.dcgp_multiclass_varexp_grad(_lib.ptr(Fm), _lib.ptr(Fv), _lib.ptr(Yd), S, N, K, lik.epsilon, coef,
                                                         _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
         grads = [None] * len(model.layers)
+        main = torch.cuda.current_stream(model.device)
+        if self._side is None:
+            self._side = [torch.cuda.Stream(device=model.device) for _ in model.layers]
+        # (1) the minibatch-sized backward of every layer, top to bottom, queued back to back on the main stream
+        done = [None] * len(model.layers)
         for i in range(len(model.layers) - 1, -1, -1):
             first = (i == 0)
             Xin = X if first else Fs[i - 1].reshape(S * N, -1)
             gX = self.bwd[i].t_sized(Xin, S if first else 1, g_mean, g_var, need_gX=not first)
-            grads[i] = self.bwd[i].m_only(kl_weight=1.0 / wsize)
+            done[i] = torch.cuda.Event()
+            done[i].record(main)
             if not first:
                 n = gX.numel()
                 g_mean, g_var = torch.empty_like(gX), torch.empty_like(gX)
@@ -151,6 +216,17 @@ class ElboGradient(object):
                 vprev = Fvars[i - 1].reshape(-1).contiguous()
                 _lib.check(_lib.lib.dcgp_sample_backward(_lib.ptr(gX), _lib.ptr(zprev), _lib.ptr(vprev), n, JITTER,
                                                          _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
+        # (2) the M-only chain rule of each layer on its own side stream: it only needs that layer's dQ / dbeta and
+        #     overlaps with the minibatch-sized work still running below it
+        for i in range(len(model.layers) - 1, -1, -1):
+            self._side[i].wait_event(done[i])
+            with torch.cuda.stream(self._side[i]):
+                grads[i] = self.bwd[i].m_only(kl_weight=1.0 / wsize)
+                for t in grads[i].values():
+                    if isinstance(t, torch.Tensor):
+                        t.record_stream(main)      # consumed by Adam on the main stream
+        for side in self._side:
+            main.wait_stream(side)
         return elbo, grads
 
 
