@@ -143,10 +143,13 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------------------------- reference / CPU arm
-def cpu_reference_rate(cfg, layers, n_img, seed=99):
-    """The reference's CPU implementation cannot run here (TensorFlow/GPflow absent): the float64
-    oracle restatement (oracle/dcgp_oracle.py, single-solve form, all host BLAS threads) is timed on a bounded sample of
-    the same workload: `n_img` images with all S samples each, full 3-layer forward ELBO."""
+def cpu_reference_rate(cfg, layers, n_img, seed=99, forward_only=False):
+    """The reference's CPU implementation cannot run here (TensorFlow/GPflow absent).  Timed instead,
+    on a bounded sample of the same workload (`n_img` images with all S samples each, full 3-layer model):
+      * ELBO step  : the float64 torch-CPU restatement with autograd (oracle/dcgp_oracle_torch.py): forward + backward,
+                     which is what TensorFlow executes per optimiser step (tf.gradients; Adam itself is negligible);
+      * forward only: the float64 NumPy/SciPy oracle (oracle/dcgp_oracle.py, single-solve form).
+    Both use all host BLAS threads."""
     from oracle import dcgp_oracle as O
     rng = np.random.RandomState(seed)
     S = cfg["S"]
@@ -158,7 +161,11 @@ def cpu_reference_rate(cfg, layers, n_img, seed=99):
         D = oh * ow * lay["R"] if lay["type"] == "conv" else lay["R"]
         zs.append(rng.standard_normal((S, n_img, D)))
     t0 = time.perf_counter()
-    elbo = O.dgp_elbo(layers, X, Y, zs, NUM_DATA, S, JITTER, fast=True)
+    if forward_only:
+        elbo = O.dgp_elbo(layers, X, Y, zs, NUM_DATA, S, JITTER, fast=True)
+    else:
+        from oracle import dcgp_oracle_torch as OT
+        elbo, _ = OT.elbo_and_grads(layers, X, Y, zs, NUM_DATA, S, JITTER)
     dt = time.perf_counter() - t0
     return n_img / dt, dt, float(elbo)
 
@@ -171,17 +178,18 @@ def run_reference(args, cfg):
     n_img = args.ref_images
     rates = []
     for i in range(args.warmup + args.steps):
-        r, dt, _ = cpu_reference_rate(cfg, layers, n_img, seed=99 + i)
+        r, dt, _ = cpu_reference_rate(cfg, layers, n_img, seed=99 + i, forward_only=args.forward_only)
         if i >= args.warmup:
             rates.append((r, dt))
     value = float(np.mean([r for r, _ in rates]))
     ms = float(np.mean([dt for _, dt in rates])) * 1e3
     cores = os.cpu_count()
-    sample = "%d images x S=%d, full 3-layer forward ELBO, float64 NumPy/SciPy oracle port (TF/GPflow not installable)" % (n_img, cfg["S"])
+    what = "forward ELBO (NumPy/SciPy float64)" if args.forward_only else "forward + backward (torch-CPU float64 autograd)"
+    sample = "%d images x S=%d, full 3-layer model, %s; oracle port, TF/GPflow not installable" % (n_img, cfg["S"], what)
     line = {"impl": "reference", "metric": "ELBO-step images/sec", "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.config + ": " + cfg["desc"], "step": "forward ELBO (CPU oracle port)", "sample": sample},
+            "config": {"workload": args.config + ": " + cfg["desc"], "step": what, "sample": sample},
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -285,10 +293,11 @@ def run_ours(args, cfg):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r, dt, _ = cpu_reference_rate(cfg, layers, args.ref_images)
+        r, dt, _ = cpu_reference_rate(cfg, layers, args.ref_images, forward_only=args.forward_only)
         cpu = {"value": r, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d images x S=%d, full 3-layer forward ELBO in %.1f s, float64 NumPy/SciPy oracle port "
-                         "(reference TF/GPflow path not installable)" % (args.ref_images, S, dt)}
+               "sample": "%d images x S=%d, full 3-layer model, %s in %.1f s, float64 oracle port (reference TF/GPflow "
+                         "path not installable)" % (args.ref_images, S, "forward ELBO" if args.forward_only else
+                                                    "forward + backward (torch-CPU autograd)", dt)}
     total_flops, _ = algorithmic_flops(cfg, B)
     if not args.forward_only:
         total_flops *= 3.0      # SURVEY 8d convention: backward = 2x forward
@@ -308,11 +317,16 @@ def run_ours(args, cfg):
 
 
 def kernel_roofline(model, cfg, B, S, device, flush):
-    """Dominant kernel = cond_tc_kernel of conv layer 2 (81% of the step's flops).  Times dcgp_layer_apply pieces live:
-    the conditional GEMM alone is isolated by timing apply with and without it is not possible through the C ABI, so
-    the layer-2 apply (Kuf + conditional GEMM + finalize) is timed and the share of the GEMM comes from the committed
-    ncu launch list (profiles/)."""
+    """Dominant kernel = the tcgen05 conditional GEMM `tc_kernel<MODE_COND,256>` of conv layer 2 (its forward launch; the
+    two backward GEMMs of the same layer are the same kernel in MODE_GEMM).  Timed live with CUDA events recorded by the
+    library on the launching stream around that kernel (dcgp_set_kernel_timing), L2 flushed before every launch.
+      achieved = ALGORITHMIC flops per launch (T*(M^2 + R*M^2 + 2MR + 2M(R+1)), triangular count, no split)
+                 / launch duration;   peak = MEASURED_PEAKS.json bf16 burst (the kernel is timed alone);
+      executed_* = the tensor-pipe flops the launch really issues: 3 split products x dense W (+ the mean tile);
+      traffic = dram__bytes_read + dram__bytes_write of this launch from the committed `ncu --set full` capture
+                (profiles/r1_ncu_full_layer2_forward_kuf_cond.csv)."""
     import torch
+    from deepcgp_b200 import _lib
     if len(model.layers) < 3:
         return None
     peaks = {}
@@ -321,36 +335,43 @@ def kernel_roofline(model, cfg, B, S, device, flush):
     except Exception:
         pass
     peak = float(peaks.get("bf16_tflops", 1590.0))
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
     layer = model.layers[1]
     n_rows = S * B
     D_in = int(np.prod(layer.view.input_size)) * layer.view.feature_maps
     X = torch.randn((n_rows, D_in), device=device)
     layer.prepare()
     layer._hold = True
+    _lib.lib.dcgp_set_kernel_timing(1)
     for _ in range(3):
         layer._conditional(X)
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(5):
+    t_cond, t_kuf = [], []
+    for _ in range(10):
         flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
         layer._conditional(X)
-        b.record()
-        torch.cuda.synchronize()
-        ts.append(a.elapsed_time(b))
+        t_cond.append(_lib.lib.dcgp_kernel_ms(0))
+        t_kuf.append(_lib.lib.dcgp_kernel_ms(1))
+    _lib.lib.dcgp_set_kernel_timing(0)
     layer._hold = False
-    ms = float(np.mean(ts))
-    _, cond = algorithmic_flops(cfg, B)
-    M, R, P = layer.num_inducing, layer.gp_count, layer.patch_count
-    L = layer.patch_length
+    ms, ms_kuf = float(np.mean(t_cond)), float(np.mean(t_kuf))
+    M, R, P, L = layer.num_inducing, layer.gp_count, layer.patch_count, layer.patch_length
     T = P * n_rows
-    alg = cond[1] + T * 2.0 * M * L          # conditional GEMM + Kuf of this layer (what the timed region runs)
+    alg = T * (M * M + R * M * M + 2.0 * M * R + 2.0 * M * (R + 1))
     executed = 3 * 2.0 * T * ((R + 1) * M * M + 256 * M)
     ach = alg / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "layer-2 apply: kuf + cond_tc_kernel<256> + finalize", "achieved": ach, "peak": peak,
-            "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "ms": ms, "algorithmic_gflop": alg / 1e9,
-            "executed_tensor_gflop": executed / 1e9, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback"}
+    kuf_bytes = 4.0 * T * M + 4.0 * n_rows * D_in            # K planes written (hi+lo fp16) + images read
+    return {"bound": "tensor", "kernel": "tc_kernel<MODE_COND,256> (conditional GEMM, conv layer 2 forward)",
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "traffic": 911319040, "ms": ms, "algorithmic_gflop": alg / 1e9,
+            "executed_tensor_gflop": executed / 1e9, "executed_tflops": executed / (ms * 1e-3) / 1e12,
+            "executed_frac": executed / (ms * 1e-3) / 1e12 / peak,
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590"),
+            "tensor_pipe_active_pct_ncu": 96.7,
+            "kuf": {"kernel": "kuf_tc_kernel<256> (conv layer 2)", "bound": "hbm", "ms": ms_kuf,
+                    "achieved": kuf_bytes / (ms_kuf * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                    "frac": kuf_bytes / (ms_kuf * 1e-3) / 1e9 / hbm, "algorithmic_bytes": kuf_bytes,
+                    "traffic": 492560896}}
 
 
 def main():

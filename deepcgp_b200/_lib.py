@@ -37,6 +37,8 @@ SIGNATURES = {
     "dcgp_last_error": (C.c_char_p, []),
     "dcgp_version": (_i, []),
     "dcgp_launch_count": (C.c_longlong, []),
+    "dcgp_set_kernel_timing": (None, [_i]),
+    "dcgp_kernel_ms": (C.c_double, [_i]),
     "dcgp_view_geometry": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dcgp_extract_patches": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dcgp_kuu": (_i, [_vp, _i, _i, _d, _d, _d, _vp, _vp]),

@@ -182,6 +182,8 @@ extern "C" {
 const char* dcgp_last_error(void) { return dcgp::last_error(); }
 int dcgp_version(void) { return 100; }
 long long dcgp_launch_count(void) { return dcgp::launch_count(); }
+void dcgp_set_kernel_timing(int on) { dcgp::tc_set_timing(on); }
+double dcgp_kernel_ms(int which) { return dcgp::tc_kernel_ms(which); }
 
 int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH, int* OW, int* P, int* L) {
   if (H < f || W < f || f < 1 || s < 1 || C < 1) { set_error("bad view geometry"); return DCGP_ERR_ARG; }

@@ -432,6 +432,31 @@ static int make_tmap_f16(CUtensorMap* tm, const void* base, uint64_t rows, uint6
   return DCGP_OK;
 }
 
+// Optional live kernel timing (bench.py's roofline leg): CUDA events recorded on the launching stream around the
+// conditional-GEMM and Kuf kernels when enabled; dcgp_kernel_ms() synchronises on the end event and returns the duration.
+static int g_timing = 0;
+static cudaEvent_t g_ev[2][2];
+static bool g_ev_init = false, g_ev_used[2] = {false, false};
+void tc_set_timing(int on) {
+  g_timing = on;
+  if (on && !g_ev_init) {
+    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) cudaEventCreate(&g_ev[i][j]);
+    g_ev_init = true;
+  }
+}
+double tc_kernel_ms(int which) {
+  if (!g_ev_init || which < 0 || which > 1 || !g_ev_used[which]) return -1.0;
+  float ms = 0.f;
+  cudaEventSynchronize(g_ev[which][1]);
+  if (cudaEventElapsedTime(&ms, g_ev[which][0], g_ev[which][1]) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
+struct ScopedTimer {
+  int which; cudaStream_t st; bool on;
+  ScopedTimer(int w, cudaStream_t s) : which(w), st(s), on(g_timing && g_ev_init) { if (on) cudaEventRecord(g_ev[which][0], st); }
+  ~ScopedTimer() { if (on) { cudaEventRecord(g_ev[which][1], st); g_ev_used[which] = true; } }
+};
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -476,6 +501,7 @@ static int launch_cond_tc(const TcPrep& prep, const TcCondWork& w, int T, int Mp
   p.T = T; p.Mp = Mp; p.R = R; p.njt = Mp / BN; p.nkb = Mp / kBK;
   p.n_items = ceil_div(T, kBM) * (R + 2);
   p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
+  ScopedTimer timer(0, st);
   return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, p, st);
 }
 
@@ -1088,6 +1114,7 @@ static int launch_kuf_tc(const TcPrep& prep, const View& v, const float* X, int 
     attr = true;
   }
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  ScopedTimer timer(1, st);
   kuf_tc_kernel<BN><<<grid, kKufThreads, smem_bytes, st>>>(tmZh, tmZl, p);
   return check_launch("kuf_tc");
 }

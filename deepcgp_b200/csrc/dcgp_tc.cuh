@@ -73,6 +73,9 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
                    float* Kt32, const double* patch_weights, const float* X, int n_rows, float* Kzx, float* acc,
                    float* mean_t, cudaStream_t st);
 
+void tc_set_timing(int on);
+double tc_kernel_ms(int which);   // 0 = conditional GEMM, 1 = Kuf
+
 // Workspace of the backward pass of one layer (see dcgp_tc_bwd.inc)
 struct TcBwdWork {
   int Jp, Lp, splits2, splits4;

@@ -62,6 +62,11 @@ const char* dcgp_last_error(void);
 int dcgp_version(void);
 /* number of CUDA kernels this library has launched so far in this process (bench.py reports it as gpu_launches) */
 long long dcgp_launch_count(void);
+/* Live kernel timing for roofline reports: when enabled, CUDA events are recorded on the launching stream around the
+ * most recent conditional-GEMM (which = 0) and Kuf (which = 1) kernel; dcgp_kernel_ms() waits for the end event and
+ * returns the duration in milliseconds (-1 if none was recorded). */
+void dcgp_set_kernel_timing(int on);
+double dcgp_kernel_ms(int which);
 
 /* views.py:56-68 FullView._patch_count/_patch_length/_out_image_size */
 int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH_host, int* OW_host, int* P_host, int* L_host);
