@@ -9,6 +9,7 @@
 //      x = hi + lo (22 mantissa bits), G ~= Kh*Wh + Kh*Wl + Kl*Wh  -> three MMAs per k-step (lo*lo ~ 2^-22 dropped).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dcgp_tc.cuh"
@@ -679,34 +680,34 @@ __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, cons
   }
 }
 
-// QB planes [Mp, Jp]: row m = [2 Q_0[m,:] | 2 Q_1[m,:] | ... | 2 Q_R[m,:] | beta[m, 0..R) | 0...], Q_0 = Kuu^-1 (float64),
-// Q_r (float32, symmetric).  One common scale from mx2 = {max|Q| , max|beta|}; thread 0 publishes {scale, 1/scale}.
-__global__ void pack_qb_f16_kernel(const double* __restrict__ Kinv, const float* __restrict__ Qr, const double* __restrict__ beta,
-                                   int M, int Mp, int R, const float* __restrict__ mx2, float* __restrict__ scal2,
-                                   __half* __restrict__ QBh, __half* __restrict__ QBl) {
-  const float mmax = fmaxf(2.f * mx2[0], mx2[1]);
+// QP planes [R*Mp + 256, Mp]: row (r-1)*Mp + i = 2 (Q_r[i,:] - Q_0[i,:]), Q_0 = Kuu^-1 (float64), Q_r float32 (symmetric);
+// the remaining rows are zero.  Scale from the bound 4 * max(|Q_r|, |Q_0|); thread 0 publishes {scale, 1/scale}.
+// Also writes beta32 [Mp, 64] for the mean path of the distance-gradient kernel.
+__global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float* __restrict__ Qr, const double* __restrict__ beta,
+                                   int M, int Mp, int R, const float* __restrict__ mxq, float* __restrict__ scal2,
+                                   __half* __restrict__ QPh, __half* __restrict__ QPl, float* __restrict__ beta32) {
+  const float mmax = 4.f * mxq[0];
   int ex = 0;
   if (mmax > 0.f && isfinite(mmax)) frexpf(mmax, &ex);
   const double sc = (double)ldexpf(1.f, 14 - ex);
   if (blockIdx.x == 0 && threadIdx.x == 0) { scal2[0] = (float)sc; scal2[1] = (float)(1.0 / sc); }
-  const long long Jp = (long long)(R + 1) * Mp + 64;
-  const long long total = (long long)Mp * Jp;
+  const long long rows = (long long)R * Mp + 256;
+  const long long total = rows * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long j = e % Jp;
-    const int m = (int)(e / Jp);
+    const int j = (int)(e % Mp);
+    const long long row = e / Mp;
     double v = 0.0;
-    if (m < M) {
-      if (j < (long long)(R + 1) * Mp) {
-        const int blk = (int)(j / Mp), mm = (int)(j % Mp);
-        if (mm < M) v = 2.0 * sc * (blk == 0 ? Kinv[(long long)m * M + mm] : (double)Qr[((long long)(blk - 1) * Mp + m) * Mp + mm]);
-      } else {
-        const int r = (int)(j - (long long)(R + 1) * Mp);
-        if (r < R) v = sc * beta[(long long)m * R + r];
-      }
+    if (row < (long long)R * Mp) {
+      const int r = (int)(row / Mp), i = (int)(row % Mp);
+      if (i < M && j < M) v = 2.0 * sc * ((double)Qr[((long long)r * Mp + i) * Mp + j] - Kinv[(long long)i * M + j]);
     }
     const __half hi = __float2half_rn((float)v);
-    QBh[e] = hi;
-    QBl[e] = __float2half_rn((float)(v - (double)__half2float(hi)));
+    QPh[e] = hi;
+    QPl[e] = __float2half_rn((float)(v - (double)__half2float(hi)));
+    if (e < (long long)Mp * 64) {
+      const int m = (int)(e / 64), rr = (int)(e % 64);
+      beta32[e] = (m < M && rr < R) ? (float)beta[(long long)m * R + rr] : 0.f;
+    }
   }
 }
 
@@ -758,11 +759,9 @@ void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   t.BRh = c.take((size_t)R * Mp * Mp * 2);
   t.BRl = c.take((size_t)R * Mp * Mp * 2);
   t.Br32 = (float*)c.take((size_t)R * Mp * Mp * 4);
-  {
-    const size_t Jp = (size_t)(R + 1) * Mp + 64;
-    t.QBh = c.take((size_t)Mp * Jp * 2);
-    t.QBl = c.take((size_t)Mp * Jp * 2);
-  }
+  t.QBh = c.take(((size_t)R * Mp + 256) * Mp * 2);
+  t.QBl = c.take(((size_t)R * Mp + 256) * Mp * 2);
+  t.beta32 = (float*)c.take((size_t)Mp * 64 * 4);
   t.ZTh = c.take((size_t)t.Lp * Mp * 2);
   t.ZTl = c.take((size_t)t.Lp * Mp * 2);
   t.Wmh = t.Wml = nullptr;
@@ -858,7 +857,8 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
     if ((rc = maxabs_f32(t.Br32, (long long)R * Mp * Mp, t.mx + 5, st))) return rc;
     if ((rc = maxabs_f64(Kinv, M, M, M, 0, t.mx + 5, st))) return rc;
     if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 6, st))) return rc;
-    pack_qb_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Kinv, t.Br32, beta, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl);
+    pack_qp_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Kinv, t.Br32, beta, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl,
+                                                      t.beta32);
     if ((rc = check_launch("tc_build_backward_operands", 3))) return rc;
   }
   return DCGP_OK;

@@ -22,7 +22,8 @@ struct TcPrep {
   // ---- operands of the backward pass
   void *BRh, *BRl;   // [R*Mp, Mp]   B_r = W_r^T = G L_r
   float* Br32;       // [R*Mp, Mp]   (also reused for Q_r = B_r B_r^T)
-  void *QBh, *QBl;   // [Mp, Jp]     rows m: [2 Q_0[m,:] | ... | 2 Q_R[m,:] | beta[m,:] | 0], Jp = (R+1)*Mp + 64
+  void *QBh, *QBl;   // [R*Mp + 256, Mp]  QP_r = 2 (Q_r - Q_0) stacked over r = 1..R (B operand of the dK GEMM), zero padded
+  float* beta32;     // [Mp, 64]     beta[m, r] (fp32), zero padded
   void *ZTh, *ZTl;   // [Lp, Mp]     (Z / lengthscale)^T * kXScale
   size_t bytes;
 };
@@ -78,11 +79,12 @@ double tc_kernel_ms(int which);   // 0 = conditional GEMM, 1 = Kuf
 
 // Workspace of the backward pass of one layer (see dcgp_tc_bwd.inc)
 struct TcBwdWork {
-  int Jp, Lp, splits2, splits4;
+  int Jp, Lp, splits2, splits4, splitsb;
   size_t Tpad, Tkpad;
-  float *gm, *s, *gknn, *scal, *dK32, *part2, *rowsum, *rowdot, *DDZ, *part4;
-  double *colsum, *DDX;
-  void *KSh, *KSl, *KSTh, *KSTl, *KTh, *KTl, *Dh, *Dl, *DTh, *DTl, *PTh, *PTl;
+  float *gm, *s, *sT, *gmT32, *gknn, *scal, *dK32, *part2, *partb, *rowsum, *rowdot, *DDZ, *part4;
+  double *colsum, *DDX, *redpart;
+  float* colpart;
+  void *GTh, *GTl, *KTh, *KTl, *Dh, *Dl, *DTh, *DTl, *PTh, *PTl;
   size_t bytes;
 };
 void tc_carve_bwd(TcBwdWork& b, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, int P, void* buf);
