@@ -59,7 +59,7 @@ static Prep carve_prep(const dcgp_layer_desc* d, void* buf) {
 struct F64Work {
   int M, Mq, R;
   double *Kuu, *invD, *Linv, *Kinv, *Wr, *beta, *Lpinv, *invDp, *tmpMR, *tmpK, *sc;
-  void* trws;
+  void *trws, *trws2;
   size_t bytes;
 };
 
@@ -73,6 +73,7 @@ static F64Work carve_f64(int M, int R, void* ws) {
   w.invD = c.take<double>(potrf_ws_bytes(M) / sizeof(double));
   w.Linv = c.take<double>((size_t)w.Mq * w.Mq);
   w.trws = c.take<double>(trtri_ws_bytes(M) / sizeof(double));
+  w.trws2 = c.take<double>(trtri_ws_bytes(M) / sizeof(double));
   w.Kinv = c.take<double>((size_t)M * M);      // also holds Kuu(Z_prior) / its Cholesky factor for the KL
   w.Wr = c.take<double>((size_t)R * M * M);    // also reused as Lp^-1 L_r for the KL trace
   w.beta = c.take<double>((size_t)M * R);
@@ -162,6 +163,28 @@ static int kl_terms(const F64Work& w, int white, const double* Lp, int ldp, cons
   }
   DCGP_TRY(logdiag2_f64(q_sqrt, M, M, R, (long long)M * M, w.sc + 2, st));
   return launch_kl(w.sc, M, R, white, kl, st);
+}
+
+// The KL prior of a ConvLayer needs a second, independent Cholesky + inverse (Kuu at the initial Z).  Both chains are
+// latency-bound (a handful of CTAs), so the prior chain is forked onto an auxiliary stream and joined before the KL.
+// One (stream, 2 events) triple per calling stream slot, created lazily; this is the only device-side state the library keeps.
+struct AuxFork {
+  cudaStream_t aux = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static AuxFork& aux_for(cudaStream_t st) {
+  static AuxFork pool[8];
+  static cudaStream_t owner[8] = {nullptr};
+  static int used = 0;
+  for (int i = 0; i < used; ++i) if (owner[i] == st) return pool[i];
+  const int i = used < 8 ? used++ : 7;
+  owner[i] = st;
+  if (!pool[i].aux) {
+    cudaStreamCreateWithFlags(&pool[i].aux, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&pool[i].fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&pool[i].join, cudaEventDisableTiming);
+  }
+  return pool[i];
 }
 
 static int check_desc(const dcgp_layer_desc* d) {
@@ -316,17 +339,22 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
   // App. C3); SVGP_Layer: the current Ku (DS/layers.py:242-256).
   const bool own_prior = (d->kind == DCGP_LAYER_CONV) && Z_prior && Z_prior != Z && !d->white;
   GInfo gi;
-  DCGP_TRY(factor_and_G(w, d->white, q_mu, info, &gi, st));
   const double* Lp = w.Kuu;        // Cholesky factor of the prior covariance and its inverse
   const double* Lpinv = w.Linv;
   double* Kp = w.Wr;               // scratch that is free at this point on both paths
-  if (own_prior) {
-    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, Kp, st));
-    DCGP_TRY(potrf_f64(Kp, M, M, w.invDp, info, st));
-    DCGP_TRY(trtri_f64(Kp, M, M, w.invDp, w.Lpinv, w.trws, st));
+  if (own_prior) {                 // forked: runs concurrently with the Kuu chain below
+    AuxFork& ax = aux_for(st);
+    cudaEventRecord(ax.fork, st);
+    cudaStreamWaitEvent(ax.aux, ax.fork, 0);
+    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, Kp, ax.aux));
+    DCGP_TRY(potrf_f64(Kp, M, M, w.invDp, info, ax.aux));
+    DCGP_TRY(trtri_f64(Kp, M, M, w.invDp, w.Lpinv, w.trws2, ax.aux));
+    cudaEventRecord(ax.join, ax.aux);
     Lp = Kp;
     Lpinv = w.Lpinv;
   }
+  DCGP_TRY(factor_and_G(w, d->white, q_mu, info, &gi, st));
+  if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
   if (algo == DCGP_ALGO_TC) {
     if (d->white) {   // Q_0 = Kuu^-1 is needed by the backward operands even when G = Lm^-1
       GemmF64 g{};
@@ -349,6 +377,17 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
   DCGP_TRY(launch_pack_w(w.Linv, w.Mq, w.Wr, M, p.Mp, R, p.W, st));
   DCGP_TRY(launch_pack_wmean(w.beta, M, p.Mp, R, p.RP, p.Wmean, st));
   return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st);
+}
+
+int dcgp_prepare_workspace_layout(const dcgp_layer_desc* d, size_t* off_kinv, size_t* off_linv, size_t* off_lpinv, int* ld_inv) {
+  if (check_desc(d)) return DCGP_ERR_ARG;
+  char* const fake = (char*)(uintptr_t)(1u << 20);       // carve against a fake (256-B aligned) base to read the offsets back
+  F64Work w = carve_f64(d->M, d->R, fake);
+  if (off_kinv) *off_kinv = (size_t)((char*)w.Kinv - fake);
+  if (off_linv) *off_linv = (size_t)((char*)w.Linv - fake);
+  if (off_lpinv) *off_lpinv = (size_t)((char*)w.Lpinv - fake);
+  if (ld_inv) *ld_inv = w.Mq;
+  return DCGP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- layer apply

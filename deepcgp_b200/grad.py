@@ -46,6 +46,7 @@ class LayerBackward(object):
         self.gscal = torch.zeros(4, dtype=torch.float64, device=dev)
         self.gw = torch.zeros(layer._view.patch_count, dtype=torch.float64, device=dev)
         self.ws = _lib.Workspace()
+        self._offs = None
 
     def t_sized(self, X, n_rep, g_mean, g_var, need_gX):
         """dcgp_layer_backward -> gX (or None); fills gQB, gZ, gscal, gw."""
@@ -90,6 +91,20 @@ class LayerBackward(object):
         gZ = -(Hs.sum(1, keepdim=True) * Z - Hs @ Z) / (ls * ls)
         return gvar, gls, gZ
 
+    def _forward_inverses(self):
+        """Views of Kuu^-1 [M,M] and Lp^-1 [M,M] inside the workspace of the layer's last dcgp_layer_prepare."""
+        import ctypes as C
+        layer, M = self.layer, self.M
+        if self._offs is None:
+            ok, ol, op, ld = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int()
+            _lib.check(_lib.lib.dcgp_prepare_workspace_layout(layer._desc(), C.byref(ok), C.byref(ol), C.byref(op), C.byref(ld)))
+            self._offs = (ok.value, ol.value, op.value, ld.value)
+        ok, ol, op, ld = self._offs
+        ws = layer._ws.get("prep", 0, layer.device)
+        Kinv = ws[ok:ok + M * M * 8].view(torch.float64).view(M, M)
+        Lpinv = ws[op:op + ld * ld * 8].view(torch.float64).view(ld, ld)[:M, :M]
+        return Kinv, Lpinv
+
     @torch.no_grad()
     def _m_only_closed_form(self, kl_weight):
         """Non-whitened case, written out as ~15 batched float64 GEMMs (no autograd graph, no triangular solves):
@@ -105,9 +120,8 @@ class LayerBackward(object):
         q_mu, Lq = layer.q_mu, torch.tril(layer.q_sqrt)
         eye = torch.eye(M, dtype=torch.float64, device=dev)
         Kn, D = self._rbf_parts(Z, var, ls)
-        # cholesky_ex: no host-side error check (torch.linalg.cholesky synchronises to read `info`); the forward's own
-        # Cholesky already reports a non-PD Kuu through the layer's device-side info flag
-        Kinv = torch.cholesky_inverse(torch.linalg.cholesky_ex(Kn + JITTER * eye, check_errors=False)[0])
+        # Kuu^-1 and the prior's Lp^-1 were already formed (float64) by this step's dcgp_layer_prepare: re-use them
+        Kinv, Lpinv = self._forward_inverses()
         B = Kinv @ Lq                                                    # [R,M,M]
         U = (gQ[1:] + gQ[1:].transpose(1, 2)) @ B                        # d/dB_r
         gLq = Kinv @ U                                                   # d/dL_r (through B_r)
@@ -118,7 +132,7 @@ class LayerBackward(object):
         if conv:    # prior = Kuu at the initial Z (a constant) with the live hyper-parameters (layers.py:149-150)
             Zp = layer.Z_prior.to(torch.float64)
             Kpn, Dp = self._rbf_parts(Zp, var, ls)
-            Kpinv = torch.cholesky_inverse(torch.linalg.cholesky_ex(Kpn + JITTER * eye, check_errors=False)[0])
+            Kpinv = Lpinv.T @ Lpinv
             C = Kpinv @ Lq
             a = Kpinv @ q_mu
         else:
