@@ -13,11 +13,14 @@ from tests.util import golden_names, layers_from_golden, load_golden
 pytestmark = pytest.mark.gpu
 
 
-def _check(name, got, ref, tol=2e-3):
+def _check(name, got, ref, tol=2e-3, floor=1e-5):
+    """max|got - ref| <= tol * max|ref| + floor.  The floor only matters for gradients that vanish analytically (e.g. the
+    patch-weight gradient when every class has the same predictive variance: sum_r dELBO/dvar_r = 0 exactly, while the
+    float32 upstream gradients, each of size ~ num_data/N, cancel only to ~1e-7 relative); callers scale it with num_data/N."""
     got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
-    scale = max(np.max(np.abs(ref)), 1e-12)
-    err = np.max(np.abs(got.reshape(ref.shape) - ref)) / scale
-    assert err <= tol, "%s: max|diff|/max|ref| = %.3e (ref max %.3e)" % (name, err, scale)
+    scale = np.max(np.abs(ref))
+    err = np.max(np.abs(got.reshape(ref.shape) - ref))
+    assert err <= tol * scale + floor, "%s: max|diff| = %.3e, max|ref| = %.3e" % (name, err, scale)
 
 
 @pytest.mark.parametrize("name", golden_names("dgp"))
@@ -38,7 +41,7 @@ def test_elbo_gradient_vs_autograd_oracle(name):
     assert abs(elbo - ref_elbo) <= 1e-3 * abs(ref_elbo)
     for i, (got, ref) in enumerate(zip(grads, ref_grads)):
         for k, v in ref.items():
-            _check("layer %d %s" % (i, k), npy(got[k]), v)
+            _check("layer %d %s" % (i, k), npy(got[k]), v, floor=2e-8 * float(g["num_data"]) / X32.shape[0])
 
 
 def test_varexp_grad_matches_autograd():
@@ -96,3 +99,26 @@ def test_training_steps_increase_the_elbo():
         elbos.append(float(elbo.item()))
         opt.step(grads)
     assert elbos[-1] > elbos[0], elbos
+
+
+def test_elbo_gradient_cfg2_shape_vs_autograd_oracle():
+    """BASELINE config 2 shapes (MNIST 2-layer DCGP: 28x28x1, f=5 s=2 -> 12x12x10, f=5 s=1; M=128,128; R=10), reduced batch:
+    ELBO and every parameter gradient against float64 autograd of the oracle."""
+    import bench
+    import deepcgp_b200 as D
+    from oracle import dcgp_oracle_torch as OT
+    cfg = dict(bench.CONFIGS["cfg2"])
+    layers = bench.synth_params(cfg, seed=77)
+    rng = np.random.RandomState(5)
+    N, S = 4, 3
+    X32 = rng.standard_normal((N, 28 * 28)).astype(np.float32)
+    Y = rng.randint(0, 10, size=(N, 1))
+    dims = [144 * 10, 10]
+    zs32 = [rng.standard_normal((S, N, d)).astype(np.float32) for d in dims]
+    ref_elbo, ref_grads = OT.elbo_and_grads(layers, X32.astype(np.float64), Y, [z.astype(np.float64) for z in zs32], 60000.0, S)
+    model = build_model(layers, X32, Y, S, 60000.0, "tc")
+    elbo, grads = D.ElboGradient(model)(X32, Y, zs=[torch.as_tensor(z, device=dev()) for z in zs32])
+    assert abs(float(elbo.item()) - ref_elbo) <= 1e-3 * abs(ref_elbo)
+    for i, (got, ref) in enumerate(zip(grads, ref_grads)):
+        for k, v in ref.items():
+            _check("layer %d %s" % (i, k), npy(got[k]), v, floor=2e-8 * 60000.0 / N)
