@@ -878,7 +878,8 @@ int tc_gemm_splits(const TcGemm& g) {
 // Roles: 4 gather warps (im2col rows -> split fp16 -> SWIZZLE_128B smem, + the TMA loads of the Z planes), 1 MMA warp,
 // 4 epilogue warps (TMEM -> exp -> split-fp16 planes of K, the A operand of the conditional GEMM).  Patches never touch HBM.
 constexpr float kXScale = 256.f;             // fixed power-of-two pre-scale of xs and zs before the fp16 split
-constexpr int kKufThreads = 288;             // warps 0-3 gather, warp 4 MMA, warps 5-8 epilogue
+constexpr int kKufGatherWarps = 8, kKufEpiWarps = 8;
+constexpr int kKufThreads = 32 * (kKufGatherWarps + 1 + kKufEpiWarps);   // warps 0-7 gather, warp 8 MMA, warps 9-16 epilogue
 
 struct KufParams {
   const float* X;      // [n_rows, HWC]
@@ -905,41 +906,59 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
-  float* xx_s = (float*)(tmem_base_smem + 4);     // [4][128] squared norms of the tile's patches (ring over tiles)
+  float* xx_s = (float*)(tmem_base_smem + 4);     // [4 tiles][128] squared norms of the tile's patches (ring over tiles)
+  int* off_s = (int*)(xx_s + 4 * 2 * kBM);        // [nkb*64] image offset of patch element l (im2col index math, once per CTA)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.v.L;
 
+  for (int l = threadIdx.x; l < p.nkb * kBK; l += kKufThreads) off_s[l] = (l < L) ? p.v.elem_off(l) : 0;
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmZ_hi); tma_prefetch_desc(&tmZ_lo);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }   // 4 gather warps + TMA
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], kKufGatherWarps + 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * kKufEpiWarps); }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 4) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  if (warp == kKufGatherWarps) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_smem;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ gather: one patch row per thread
-    const int r = threadIdx.x;                      // 0..127
-    const int fC = p.v.f * p.v.C, rowstride = p.v.W * p.v.C;
+  if (warp < kKufGatherWarps) {
+    // ------------------------------------------------------------------ gather: one WARP per patch row and k-block
+    // Lane i owns elements 2i, 2i+1 of the row's 64-element k-block slice, so a warp-level load walks the (dx, c)-contiguous
+    // runs of the NHWC image (coalesced), and its 32 x 4-byte shared-memory stores fill exactly one swizzled 128-byte row.
+    const int gw = warp;                              // 0..7: rows gw*16 .. gw*16+15 of the tile
     int stage = 0; uint32_t phase = 0; uint32_t tile = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
       const int tt = item / p.njt, jt = item - tt * p.njt;
-      const int t = tt * kBM + r;
-      const bool valid = t < p.T;
-      const float* src = p.X;
-      if (valid) {
-        const int n = t / p.v.P, pp = t - n * p.v.P;
-        src += (long long)n * p.v.HWC + p.v.patch_base(pp);
+      // per-row image base (lanes 0..15 compute the warp's 16 rows, broadcast by shuffle below); -1 marks rows beyond T
+      long long my_base = -1;
+      if (lane < 16) {
+        const int t = tt * kBM + gw * 16 + lane;
+        if (t < p.T) {
+          const int n = t / p.v.P, pp = t - n * p.v.P;
+          my_base = (long long)n * p.v.HWC + p.v.patch_base(pp);
+        }
       }
-      float xx = 0.f;
-      int dy = 0, q = 0;                            // patch element l = dy * fC + q
+      float xxp[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) xxp[i] = 0.f;
       for (int kb = 0; kb < p.nkb; ++kb) {
+        const int l = kb * kBK + 2 * lane;
+        const int o0 = off_s[l], o1 = off_s[l + 1];
+        const bool in0 = l < L, in1 = l + 1 < L;
+        float x0[16], x1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                // all 32 loads of the k-block in flight before the slot wait
+          const long long base = __shfl_sync(0xffffffffu, my_base, i);
+          const float* src = p.X + (base < 0 ? 0 : base);
+          const float msk = base < 0 ? 0.f : p.inv_ls;
+          x0[i] = in0 ? __ldg(src + o0) * msk : 0.f;
+          x1[i] = in1 ? __ldg(src + o1) * msk : 0.f;
+        }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * Cfg::kStageBytes;
         if (threadIdx.x == 0) {
@@ -947,37 +966,35 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
           tma_load_2d(st + 2 * Cfg::kStageA, &tmZ_hi, &full_bar[stage], kb * kBK, jt * BN);
           tma_load_2d(st + 2 * Cfg::kStageA + Cfg::kStageB, &tmZ_lo, &full_bar[stage], kb * kBK, jt * BN);
         }
-        const int l0 = kb * kBK;
-        int nchunk = (L - l0 + 7) >> 3;             // 16-byte chunks (8 elements) that hold data
-        nchunk = nchunk > 8 ? 8 : ((nchunk + 1) & ~1);   // whole 16-element k-steps
-        uint8_t* rowh = st + (r >> 3) * 1024 + (r & 7) * 128;
-        uint8_t* rowl = rowh + Cfg::kStageA;
-        for (int c = 0; c < nchunk; ++c) {
-          __half hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float x = 0.f;
-            if (valid && l0 + c * 8 + e < L) {
-              x = __ldg(src + dy * rowstride + q) * p.inv_ls;
-              if (++q == fC) { q = 0; ++dy; }
-            }
-            xx = fmaf(x, x, xx);
-            const float xsx = x * kXScale;
-            hi[e] = __float2half_rn(xsx);
-            lo[e] = __float2half_rn(xsx - __half2float(hi[e]));
-          }
-          const int pc = (c ^ (r & 7)) * 16;        // SWIZZLE_128B: 16-byte chunk index XOR (row mod 8)
-          *reinterpret_cast<uint4*>(rowh + pc) = *reinterpret_cast<uint4*>(hi);
-          *reinterpret_cast<uint4*>(rowl + pc) = *reinterpret_cast<uint4*>(lo);
+        for (int i = 0; i < 16; ++i) {
+          const int r = gw * 16 + i;
+          xxp[i] = fmaf(x0[i], x0[i], fmaf(x1[i], x1[i], xxp[i]));
+          const float s0 = x0[i] * kXScale, s1 = x1[i] * kXScale;
+          const __half2 hi = __floats2half2_rn(s0, s1);
+          const float2 hf = __half22float2(hi);
+          const __half2 lo = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+          // element pair `lane` of row r: 16-byte chunk lane/4 (XOR-swizzled with r mod 8), 4-byte slot lane%4 inside it
+          uint8_t* dst = st + (r >> 3) * 1024 + (r & 7) * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
+          *reinterpret_cast<__half2*>(dst) = hi;
+          *reinterpret_cast<__half2*>(dst + Cfg::kStageA) = lo;
         }
-        if (kb == p.nkb - 1) xx_s[(tile & 3) * kBM + r] = xx;
+        if (kb == p.nkb - 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float v = xxp[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) xx_s[(tile & 3) * kBM + gw * 16 + i] = v;
+          }
+        }
         fence_proxy_async();                        // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kKufGatherWarps) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(BN);
@@ -1011,8 +1028,10 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: exp + split, one patch row per thread
-    const int q = warp & 3;
+    // ------------------------------------------------------------------ epilogue: exp + split; 2 warps per lane quarter
+    const int ew = warp - kKufGatherWarps - 1;      // 0..7
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int chalf = ew >> 2;                       // which half of the BN columns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float ks = p.kscal[0] * p.variance;
     const float dscale = 2.f / (kXScale * kXScale);
@@ -1030,18 +1049,21 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
       __half* oh = p.Kh + t * p.Mp + jt * BN;
       __half* ol = p.Kl + t * p.Mp + jt * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         float v[32];
         tmem_ld_32x32(taddr + c, v);
-        __align__(16) __half hi[32];
-        __align__(16) __half lo[32];
+        __align__(16) __half2 hi[16];
+        __align__(16) __half2 lo[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int m = jt * BN + c + i;
-          const float d = xx + __ldg(p.zz + m) - dscale * v[i];
-          const float k = (valid && m < p.M) ? ks * __expf(-0.5f * d) : 0.f;
-          hi[i] = __float2half_rn(k);
-          lo[i] = __float2half_rn(k - __half2float(hi[i]));
+        for (int i = 0; i < 16; ++i) {
+          const int m = jt * BN + c + 2 * i;
+          const float2 zz2 = __ldg(reinterpret_cast<const float2*>(p.zz + m));
+          const float d0 = xx + zz2.x - dscale * v[2 * i], d1 = xx + zz2.y - dscale * v[2 * i + 1];
+          const float k0 = (valid && m < p.M) ? ks * __expf(-0.5f * d0) : 0.f;
+          const float k1 = (valid && m + 1 < p.M) ? ks * __expf(-0.5f * d1) : 0.f;
+          hi[i] = __floats2half2_rn(k0, k1);
+          const float2 hf = __half22float2(hi[i]);
+          lo[i] = __floats2half2_rn(k0 - hf.x, k1 - hf.y);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1055,7 +1077,7 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kKufGatherWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
@@ -1106,12 +1128,14 @@ static int launch_kuf_tc(const TcPrep& prep, const View& v, const float* X, int 
   p.n_items = ceil_div(p.T, kBM) * p.njt;
   p.nkb = ceil_div(v.L, kBK);
   p.inv_ls = inv_ls; p.variance = variance; p.zz = prep.zz; p.kscal = kscal; p.Kh = (__half*)Kh; p.Kl = (__half*)Kl;
-  constexpr int smem_bytes = Cfg::kSmemBytes + 4 * kBM * 4;
-  static bool attr = false;
+  const int smem_bytes = Cfg::kSmemBytes + 8 * kBM * 4 + ceil_div(v.L, kBK) * kBK * 4 + 64;
+  if (smem_bytes > 227 * 1024) { set_error("kuf_tc: patch length %d too large", v.L); return DCGP_ERR_ARG; }
+  static int attr_bytes = 0;
+  const bool attr = attr_bytes >= smem_bytes;
   if (!attr) {
+    attr_bytes = smem_bytes;
     cudaError_t e = cudaFuncSetAttribute(kuf_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { set_error("kuf_tc smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
-    attr = true;
   }
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   ScopedTimer timer(1, st);
