@@ -8,6 +8,7 @@
 //      Precision: the reference is float64; fp16 tensor cores with fp32 accumulation are used through a 2-way operand split
 //      x = hi + lo (22 mantissa bits), G ~= Kh*Wh + Kh*Wl + Kl*Wh  -> three MMAs per k-step (lo*lo ~ 2^-22 dropped).
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
@@ -115,6 +116,8 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
          ((uint32_t)(128 >> 4) << 24);
 }
 
+constexpr uint32_t kIdescBf16 = (1u << 7) | (1u << 10);   // a_format = b_format = BF16
+
 // ============================================================================================ K-D kernel
 constexpr int kBM = 128;      // patch-columns per tile (UMMA M, TMEM lanes)
 constexpr int kBK = 64;       // inducing points per pipeline stage (one 128-byte swizzle atom of fp16)
@@ -136,6 +139,7 @@ constexpr int MODE_GEMM = 1;   // plain batched C = A * B^T: store fp32 and/or a
 struct TcParams {
   int n_items;
   int nkb;        // K-dimension blocks of 64
+  int bf16;       // MODE_GEMM: operand planes are bf16 (hi + lo) instead of fp16
   // ---- MODE_COND
   int T;          // valid patch-columns
   int Mp;         // padded inducing points (multiple of 64)
@@ -249,7 +253,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BN);
+      const uint32_t idesc = make_idesc_f16(BN) | (p.bf16 ? kIdescBf16 : 0u);
       int stage = 0; uint32_t phase = 0;
       uint32_t tile = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -518,6 +522,7 @@ int tc_gemm(const TcGemm& g, cudaStream_t st) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.nkb = g.k_pad / kBK;
+  p.bf16 = g.bf16;
   p.m_tiles = ceil_div(g.m_pad, kBM); p.n_tiles = g.n_pad / BN;   // a 128-row box may run past a batch / the tensor: extra rows are discarded
   p.splits = g.splits > 1 ? g.splits : 1;
   p.nkb_split = ceil_div(p.nkb, p.splits);
@@ -685,7 +690,13 @@ __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, cons
 // Also writes beta32 [Mp, 64] for the mean path of the distance-gradient kernel.
 __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float* __restrict__ Qr, const double* __restrict__ beta,
                                    int M, int Mp, int R, const float* __restrict__ mxq, float* __restrict__ scal2,
-                                   __half* __restrict__ QPh, __half* __restrict__ QPl, float* __restrict__ beta32) {
+                                   __half* __restrict__ QPh, __half* __restrict__ QPl, float* __restrict__ beta32,
+                                   float* __restrict__ bscal2, __half* __restrict__ BTh, __half* __restrict__ BTl) {
+  // beta planes [Mp, 64] (the B operand of the mean-path tile of the dK GEMM), scaled from max|beta| = mxq[1]
+  int exb = 0;
+  if (mxq[1] > 0.f && isfinite(mxq[1])) frexpf(mxq[1], &exb);
+  const double sb = (double)ldexpf(1.f, 14 - exb);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { bscal2[0] = (float)sb; bscal2[1] = (float)(1.0 / sb); }
   const float mmax = 4.f * mxq[0];
   int ex = 0;
   if (mmax > 0.f && isfinite(mmax)) frexpf(mmax, &ex);
@@ -706,7 +717,11 @@ __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float*
     QPl[e] = __float2half_rn((float)(v - (double)__half2float(hi)));
     if (e < (long long)Mp * 64) {
       const int m = (int)(e / 64), rr = (int)(e % 64);
-      beta32[e] = (m < M && rr < R) ? (float)beta[(long long)m * R + rr] : 0.f;
+      const double bv = (m < M && rr < R) ? beta[(long long)m * R + rr] : 0.0;
+      beta32[e] = (float)bv;
+      const __half bh = __float2half_rn((float)(bv * sb));
+      BTh[e] = bh;
+      BTl[e] = __float2half_rn((float)(bv * sb - (double)__half2float(bh)));
     }
   }
 }
@@ -739,7 +754,7 @@ struct Carve2 {
 
 void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   memset(&t, 0, sizeof(t));
-  t.M = M; t.Mp = Mp; t.R = R; t.L = L; t.Lp = (int)align_up(L, 64);
+  t.M = M; t.Mp = Mp; t.R = R; t.L = L; t.Lp = (int)align_up(L, 64); t.LpT = (int)align_up(L + 1, 64);
   Carve2 c(buf);
   const size_t wbytes = w_rows(Mp, R) * Mp * 2;
   t.Wh = c.take(wbytes);
@@ -747,7 +762,7 @@ void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   t.Zh = c.take((size_t)Mp * t.Lp * 2);
   t.Zl = c.take((size_t)Mp * t.Lp * 2);
   t.zz = (float*)c.take((size_t)Mp * 4);
-  t.scal = (float*)c.take(16 * 4);
+  t.scal = (float*)c.take(32 * 4);
   t.mx = (float*)c.take(8 * 4);
   t.QTh = c.take((size_t)R * Mp * Mp * 2);
   t.QTl = c.take((size_t)R * Mp * Mp * 2);
@@ -762,8 +777,10 @@ void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   t.QBh = c.take(((size_t)R * Mp + 256) * Mp * 2);
   t.QBl = c.take(((size_t)R * Mp + 256) * Mp * 2);
   t.beta32 = (float*)c.take((size_t)Mp * 64 * 4);
-  t.ZTh = c.take((size_t)t.Lp * Mp * 2);
-  t.ZTl = c.take((size_t)t.Lp * Mp * 2);
+  t.ZTh = c.take((size_t)t.LpT * Mp * 2);
+  t.ZTl = c.take((size_t)t.LpT * Mp * 2);
+  t.BTh = c.take((size_t)Mp * 64 * 2);
+  t.BTl = c.take((size_t)Mp * 64 * 2);
   t.Wmh = t.Wml = nullptr;
   t.bytes = align_up(c.off, 1024);
 }
@@ -858,7 +875,7 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
     if ((rc = maxabs_f64(Kinv, M, M, M, 0, t.mx + 5, st))) return rc;
     if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 6, st))) return rc;
     pack_qp_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Kinv, t.Br32, beta, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl,
-                                                      t.beta32);
+                                                      t.beta32, t.scal + 16, (__half*)t.BTh, (__half*)t.BTl);
     if ((rc = check_launch("tc_build_backward_operands", 3))) return rc;
   }
   return DCGP_OK;
@@ -1105,12 +1122,13 @@ __global__ void pack_z_f16_kernel(const double* __restrict__ Z, int M, int Mp, i
   if (threadIdx.x == 0) zz[m] = (float)(sh[0] + sh[1] + sh[2] + sh[3]);
 }
 
-__global__ void pack_zt_f16_kernel(const double* __restrict__ Z, int M, int Mp, int L, int Lp, double inv_ls,
-                                   __half* __restrict__ ZTh, __half* __restrict__ ZTl);   // dcgp_tc_bwd.inc
+__global__ void pack_zt_bf16_kernel(const double* __restrict__ Z, int M, int Mp, int L, int Lp, double inv_ls,
+                                    __nv_bfloat16* __restrict__ ZTh, __nv_bfloat16* __restrict__ ZTl);   // dcgp_tc_bwd.inc
 
 int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st) {
   pack_z_f16_kernel<<<t.Mp, 128, 0, st>>>(Z, M, t.Mp, L, t.Lp, inv_ls, (__half*)t.Zh, (__half*)t.Zl, t.zz);
-  pack_zt_f16_kernel<<<grid_for((long long)t.Lp * t.Mp, 2048), 256, 0, st>>>(Z, M, t.Mp, L, t.Lp, inv_ls, (__half*)t.ZTh, (__half*)t.ZTl);
+  pack_zt_bf16_kernel<<<grid_for((long long)t.LpT * t.Mp, 2048), 256, 0, st>>>(Z, M, t.Mp, L, t.LpT, inv_ls, (__nv_bfloat16*)t.ZTh,
+                                                                               (__nv_bfloat16*)t.ZTl);
   set_pair_kernel<<<1, 1, 0, st>>>(kXScale, t.scal + 12);
   return check_launch("pack_z_f16", 3);
 }

@@ -8,12 +8,12 @@ namespace dcgp {
 //   x ~= (hi + lo) / 2^e  with hi = fp16(x * 2^e), lo = fp16(x * 2^e - hi): ~22 mantissa bits per operand, so that
 //   A*B ~= hi*hi + hi*lo + lo*hi on the fp16 tensor pipe with fp32 accumulation reproduces an fp32 GEMM.
 struct TcPrep {
-  int M, Mp, R, L, Lp;
+  int M, Mp, R, L, Lp, LpT;   // Lp = ceil(L/64)*64; LpT = ceil((L+1)/64)*64 (room for the ones row of ZT)
   void *Wh, *Wl;     // [(R+1)*Mp, Mp] fp16
   void *Wmh, *Wml;   // [64, Mp] fp16 (mean rows, zero padded)
   void *Zh, *Zl;     // [Mp, Lp] fp16 (Z / lengthscale)
   float* zz;         // [Mp] |z/ls|^2 (fp32, from fp64)
-  float* scal;       // [16] device {scale, 1/scale} pairs: W blocks, mean rows, q_sqrt^T, G, Lp^-1
+  float* scal;       // [32] device {scale, 1/scale} pairs: W blocks, mean rows, q_sqrt^T, G, Lp^-1, QP, kXScale, B_r, beta
   float* mx;         // [8] running max |x| per slot
   void *QTh, *QTl;   // [R*Mp, Mp] fp16: transposed q_sqrt planes (A operand of W_r = L_r^T G, B operand of Lp^-1 L_r)
   void *Gh, *Gl;     // [Mp, Mp]
@@ -24,7 +24,8 @@ struct TcPrep {
   float* Br32;       // [R*Mp, Mp]   (also reused for Q_r = B_r B_r^T)
   void *QBh, *QBl;   // [R*Mp + 256, Mp]  QP_r = 2 (Q_r - Q_0) stacked over r = 1..R (B operand of the dK GEMM), zero padded
   float* beta32;     // [Mp, 64]     beta[m, r] (fp32), zero padded
-  void *ZTh, *ZTl;   // [Lp, Mp]     (Z / lengthscale)^T * kXScale
+  void *ZTh, *ZTl;   // [LpT, Mp]    bf16 planes of (Z / lengthscale)^T * kXScale; row L = kXScale (ones row: DDZ[:, L] = row sums of dd)
+  void *BTh, *BTl;   // [Mp, 64]     fp16 planes of beta[m, r] (B operand of the mean-path tile of the dK GEMM)
   size_t bytes;
 };
 void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf);
@@ -57,6 +58,7 @@ struct TcGemm {
   float* C; long long c_batch_stride; int ldc;   // optional fp32 output (unscaled values)
   double* sq_out;                                // optional: += sum of squares of C
   float* absmax_out;                             // optional: atomic max |C| (zero it first)
+  int bf16;                                      // planes are bf16 hi/lo (unscaled values allowed) instead of fp16
   int splits; long long c_split_stride;          // split-K: partial C per split (caller reduces); splits <= 1 = off
 };
 int tc_gemm_splits(const TcGemm& g);             // number of splits tc_gemm will really use
@@ -81,10 +83,10 @@ double tc_kernel_ms(int which);   // 0 = conditional GEMM, 1 = Kuf
 struct TcBwdWork {
   int Jp, Lp, splits2, splits4, splitsb;
   size_t Tpad, Tkpad;
-  float *gm, *s, *sT, *gmT32, *gknn, *scal, *dK32, *part2, *partb, *rowsum, *rowdot, *DDZ, *part4;
-  double *colsum, *DDX, *redpart;
-  float* colpart;
-  void *GTh, *GTl, *KTh, *KTl, *Dh, *Dl, *DTh, *DTl, *PTh, *PTl;
+  float *gm, *s, *sT, *gmT32, *gknn, *scal, *dK32, *part2, *partb, *rowdot, *DDZ, *part4;
+  double *DDX, *redpart;
+  int n_redpart;
+  void *GTh, *GTl, *GMh, *GMl, *KTh, *KTl, *Dh, *Dl, *DTh, *DTl, *PTh, *PTl;   // D*, DT*, PT*: bf16 planes
   size_t bytes;
 };
 void tc_carve_bwd(TcBwdWork& b, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, int P, void* buf);
