@@ -228,16 +228,22 @@ def run_ours(args, cfg):
     elbo_host = torch.empty(1, dtype=torch.float64).pin_memory()
 
     import deepcgp_b200 as D
-    eg = D.ElboGradient(model)
-    opt = D.Adam(model, lr=args.lr)
+    if args.sequential:
+        eg = D.ElboGradient(model)
+        opt = D.Adam(model, lr=args.lr)
+    else:
+        train_step = D.TrainStep(model, lr=args.lr)
 
     def elbo_step(x, y):
-        """One optimisation step: forward ELBO, backward, (all-reduce of the flat gradient), Adam update."""
+        """One optimisation step: forward ELBO, backward, (all-reduce of the gradient), Adam update of every trainable.
+        Default = grad.TrainStep (same arithmetic as ElboGradient + Adam.step, per-layer tails overlapped)."""
         if args.forward_only:
             return model._build_likelihood(x, y, zs=zs, n_global=n_global)
-        e, grads = eg(x, y, zs=zs, n_global=n_global)
-        opt.step(grads)
-        return e
+        if args.sequential:
+            e, grads = eg(x, y, zs=zs, n_global=n_global)
+            opt.step(grads)
+            return e
+        return train_step(x, y, zs=zs, n_global=n_global)
 
     def step_resident(i):
         return elbo_step(devX[i % n_batches], devY[i % n_batches])
@@ -278,6 +284,8 @@ def run_ours(args, cfg):
     launches = _lib.lib.dcgp_launch_count() - launches0
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    if not args.forward_only and not args.sequential:
+        train_step.finish()
     for layer in model.layers:
         _lib.raise_if_not_pd(layer._info)
     elbo_val = float(model._elbo.item())
@@ -385,6 +393,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--forward-only", action="store_true", help="time the forward ELBO alone (diagnostic)")
     ap.add_argument("--lr", type=float, default=1e-3)
+    ap.add_argument("--sequential", action="store_true", help="ElboGradient + Adam.step without the per-layer pipelining (diagnostic)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

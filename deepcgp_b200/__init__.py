@@ -20,4 +20,4 @@ from .conditionals import conditional  # noqa: E402,F401
 from .layers import ConvLayer, Layer, MultiOutputConvKernel, SVGP_Layer, Zero  # noqa: E402,F401
 from .likelihoods import BroadcastingLikelihood, MultiClass  # noqa: E402,F401
 from .dgp import DGP_Base  # noqa: E402,F401
-from .grad import Adam, ElboGradient  # noqa: E402,F401
+from .grad import Adam, ElboGradient, TrainStep  # noqa: E402,F401

@@ -56,6 +56,7 @@ SIGNATURES = {
     "dcgp_layer_apply": (_i, [_pd, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dcgp_backward_workspace_bytes": (_sz, [_pd, _i, _i]),
     "dcgp_layer_backward": (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dcgp_layer_backward_phases": (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "dcgp_multiclass_varexp_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp]),
     "dcgp_sample_backward": (_i, [_vp, _vp, _vp, _sz, _d, _vp, _vp, _vp]),
     "dcgp_adam": (_i, [_vp, _vp, _vp, _vp, _sz, _d, _d, _d, _d, _i, _i, _vp]),

@@ -469,15 +469,16 @@ size_t dcgp_backward_workspace_bytes(const dcgp_layer_desc* d, int n_rows, int n
   return b.bytes + 1024;
 }
 
-int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep_buf, const void* apply_ws, const double* Z,
+int dcgp_layer_backward_phases(const dcgp_layer_desc* d, const void* prep_buf, const void* apply_ws, const double* Z,
                         const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
                         const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, void* ws,
-                        size_t ws_bytes, void* stream) {
+                        size_t ws_bytes, int phases, void* stream) {
   DCGP_TRY(check_desc(d));
   if (!prep_buf || !apply_ws || !Z || !X || !g_mean || !g_var || !gQB || !gZ || !gscal || n_rows < 1 || n_rep < 1) {
     set_error("layer_backward: bad argument");
     return DCGP_ERR_ARG;
   }
+  if (phases < 1 || phases > 3) { set_error("layer_backward: phases must be 1, 2 or 3"); return DCGP_ERR_ARG; }
   if (d->kind == DCGP_LAYER_SVGP_CONV && !gw) { set_error("layer_backward: gw required for the ConvKernel layer"); return DCGP_ERR_ARG; }
   View v; size_t Tk, T; int Mp;
   bwd_dims(d, n_rows, v, Tk, T, Mp);
@@ -488,7 +489,15 @@ int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep_buf, const vo
   Prep p = carve_prep(d, const_cast<void*>(prep_buf));
   ApplyWork a = carve_apply(d, n_rows, const_cast<void*>(apply_ws));
   return tc_layer_backward(d, v, p.tc, a.tc, b, Z, patch_weights, X, n_rows, n_rep, g_mean, g_var, gX, gQB, gZ, gscal, gw,
-                           (cudaStream_t)stream);
+                           phases, (cudaStream_t)stream);
+}
+
+int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep_buf, const void* apply_ws, const double* Z,
+                        const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
+                        const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, void* ws,
+                        size_t ws_bytes, void* stream) {
+  return dcgp_layer_backward_phases(d, prep_buf, apply_ws, Z, patch_weights, X, n_rows, n_rep, g_mean, g_var, gX, gQB, gZ, gscal,
+                                    gw, ws, ws_bytes, 3, stream);
 }
 
 int dcgp_multiclass_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,

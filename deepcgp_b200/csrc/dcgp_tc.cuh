@@ -92,6 +92,6 @@ struct TcBwdWork {
 void tc_carve_bwd(TcBwdWork& b, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, int P, void* buf);
 int tc_layer_backward(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const TcBwdWork& b,
                       const double* Z, const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
-                      const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, cudaStream_t st);
+                      const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, int phases, cudaStream_t st);
 
 }  // namespace dcgp

@@ -85,12 +85,14 @@ class DGP_Base(object):
         if self._side is None:
             self._side = [torch.cuda.Stream(device=self.device) for _ in self.layers]
         for layer, side in zip(self.layers, self._side):
+            layer._hold = True
+            if layer._pending is not None:      # grad.TrainStep pipelines this layer's update + prepare(); it is
+                continue                        # completed lazily, right before the layer is applied
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 layer.prepare()
                 layer._ready = torch.cuda.Event()
                 layer._ready.record(side)
-            layer._hold = True
         try:
             Fs, Fmeans, Fvars = self.propagate(X, full_cov=False, S=S, zs=zs)
             Fmean, Fvar = Fmeans[-1], Fvars[-1]

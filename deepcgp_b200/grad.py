@@ -48,8 +48,9 @@ class LayerBackward(object):
         self.ws = _lib.Workspace()
         self._offs = None
 
-    def t_sized(self, X, n_rep, g_mean, g_var, need_gX):
-        """dcgp_layer_backward -> gX (or None); fills gQB, gZ, gscal, gw."""
+    def t_sized(self, X, n_rep, g_mean, g_var, need_gX, phases=3):
+        """dcgp_layer_backward_phases -> gX (or None); fills gQB, gZ, gscal, gw.  phases=1 runs only what gX needs;
+        t_sized_rest() then queues the parameter-only remainder with the same arguments."""
         layer = self.layer
         d = layer._desc()
         X = _lib.f32(X, layer.device)
@@ -58,12 +59,21 @@ class LayerBackward(object):
         ws = self.ws.get("bwd", _lib.lib.dcgp_backward_workspace_bytes(d, n_rows, n_rep), layer.device)
         aws = layer._ws.get("apply", 0, layer.device)
         w = layer._patch_weights()
-        self._keep = (X, g_mean, g_var, w)
-        _lib.check(_lib.lib.dcgp_layer_backward(
+        self._keep = (X, g_mean, g_var, w, gX, ws, aws, d, n_rows, n_rep)
+        self._call(phases)
+        return gX
+
+    def t_sized_rest(self):
+        self._call(2)
+
+    def _call(self, phases):
+        layer = self.layer
+        X, g_mean, g_var, w, gX, ws, aws, d, n_rows, n_rep = self._keep
+        _lib.check(_lib.lib.dcgp_layer_backward_phases(
             d, _lib.ptr(layer._prep), _lib.ptr(aws), _lib.ptr(layer._keep[0]), _lib.ptr(w), _lib.ptr(X), n_rows, n_rep,
             _lib.ptr(g_mean), _lib.ptr(g_var), _lib.ptr(gX), _lib.ptr(self.gQB), _lib.ptr(self.gZ), _lib.ptr(self.gscal),
-            _lib.ptr(self.gw) if layer._kind == _lib.LAYER_SVGP_CONV else None, _lib.ptr(ws), ws.numel(), _lib.stream()))
-        return gX
+            _lib.ptr(self.gw) if layer._kind == _lib.LAYER_SVGP_CONV else None, _lib.ptr(ws), ws.numel(), phases,
+            _lib.stream()))
 
     def m_only(self, kl_weight=1.0):
         """Chain rule through the minibatch-independent operands; returns d ELBO / d{Z, variance, lengthscale, q_mu,
@@ -193,7 +203,8 @@ class ElboGradient(object):
         self.bwd = [LayerBackward(l) for l in model.layers]
         self._side = None
 
-    def __call__(self, X, Y, zs=None, n_global=None):
+    def _forward(self, X, Y, zs, n_global):
+        """Forward ELBO (layer outputs kept) and the gradient of the data term w.r.t. the last layer's mean / var."""
         model = self.model
         X = _lib.f32(X, model.device)
         N, S = X.shape[0], model.num_samples
@@ -202,7 +213,6 @@ class ElboGradient(object):
         zs = [_lib.f32(z, model.device) for z in zs]
         elbo = model._build_likelihood(X, Y, zs=zs, n_global=n_global, keep=True)
         Fs, Fmeans, Fvars = model._fwd
-        rank, wsize = world()
         K = Fmeans[-1].shape[2]
         coef = float(model.num_data) / float(n_global or N) / S
         Yd = torch.as_tensor(Y, device=model.device).reshape(-1).to(torch.int32).contiguous()
@@ -211,10 +221,29 @@ class ElboGradient(object):
         lik = model.likelihood.likelihood
         _lib.check(_lib.lib.dcgp_multiclass_varexp_grad(_lib.ptr(Fm), _lib.ptr(Fv), _lib.ptr(Yd), S, N, K, lik.epsilon, coef,
                                                         _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
-        grads = [None] * len(model.layers)
-        main = torch.cuda.current_stream(model.device)
         if self._side is None:
             self._side = [torch.cuda.Stream(device=model.device) for _ in model.layers]
+        return X, zs, elbo, g_mean, g_var
+
+    def _sample_backward(self, i, gX, zs):
+        """DS/utils.py:41 backward through layer i-1's reparameterised sample -> (g_mean, g_var) for layer i-1."""
+        Fvars = self.model._fwd[2]
+        n = gX.numel()
+        g_mean, g_var = torch.empty_like(gX), torch.empty_like(gX)
+        zprev = zs[i - 1].reshape(-1).contiguous()
+        vprev = Fvars[i - 1].reshape(-1).contiguous()
+        _lib.check(_lib.lib.dcgp_sample_backward(_lib.ptr(gX), _lib.ptr(zprev), _lib.ptr(vprev), n, JITTER,
+                                                 _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
+        return g_mean, g_var
+
+    def __call__(self, X, Y, zs=None, n_global=None):
+        model = self.model
+        X, zs, elbo, g_mean, g_var = self._forward(X, Y, zs, n_global)
+        Fs, Fmeans, Fvars = model._fwd
+        N, S = X.shape[0], model.num_samples
+        rank, wsize = world()
+        grads = [None] * len(model.layers)
+        main = torch.cuda.current_stream(model.device)
         # (1) the minibatch-sized backward of every layer, top to bottom, queued back to back on the main stream
         done = [None] * len(model.layers)
         for i in range(len(model.layers) - 1, -1, -1):
@@ -224,12 +253,7 @@ class ElboGradient(object):
             done[i] = torch.cuda.Event()
             done[i].record(main)
             if not first:
-                n = gX.numel()
-                g_mean, g_var = torch.empty_like(gX), torch.empty_like(gX)
-                zprev = zs[i - 1].reshape(-1).contiguous()
-                vprev = Fvars[i - 1].reshape(-1).contiguous()
-                _lib.check(_lib.lib.dcgp_sample_backward(_lib.ptr(gX), _lib.ptr(zprev), _lib.ptr(vprev), n, JITTER,
-                                                         _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
+                g_mean, g_var = self._sample_backward(i, gX, zs)
         # (2) the M-only chain rule of each layer on its own side stream: it only needs that layer's dQ / dbeta and
         #     overlaps with the minibatch-sized work still running below it
         for i in range(len(model.layers) - 1, -1, -1):
@@ -321,10 +345,11 @@ class Adam(object):
             else:
                 layer._base_kernel.lengthscales = v
 
-    def step(self, grads):
-        """grads: list (per layer) of dicts of d ELBO / d constrained parameter (this rank's share)."""
+    def _store_grads(self, grads, layer_index=None):
         for slot in self.slots:
             li, name = slot[0], slot[1]
+            if layer_index is not None and li != layer_index:
+                continue
             g = grads[li][name]
             dst = self._view(self.grad, slot)
             if name in ("variance", "lengthscale"):
@@ -332,8 +357,117 @@ class Adam(object):
                 dst.copy_((g * torch.sigmoid(u)).reshape(1))          # d softplus(u) / du
             else:
                 dst.copy_(g.reshape(dst.shape))
+
+    # ---- per-layer form used by TrainStep (same update rule; the layers' slices of the flat vector are disjoint)
+    def layer_range(self, li):
+        offs = [(s[2], s[2] + s[3]) for s in self.slots if s[0] == li]
+        return min(o[0] for o in offs), max(o[1] for o in offs)
+
+    def step_layer(self, li, grads, step_no):
+        """Adam update of layer li's slice on the CURRENT stream; returns (pinned host tensor, event) of the layer's
+        constrained (variance, lengthscale) -- they travel by value in dcgp_layer_desc, so the host needs them back."""
+        self._store_grads(grads, li)
+        lo, hi = self.layer_range(li)
+        allreduce_sum_(self.grad[lo:hi])
+        _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat[lo:hi]), _lib.ptr(self.grad[lo:hi]), _lib.ptr(self.m[lo:hi]),
+                                      _lib.ptr(self.v[lo:hi]), hi - lo, self.lr, self.b1, self.b2, self.eps, step_no, 1,
+                                      _lib.stream()))
+        hyp = [s for s in self.slots if s[0] == li and s[1] in ("variance", "lengthscale")]
+        assert hyp[0][1] == "variance" and hyp[1][2] == hyp[0][2] + 1
+        vals = torch.nn.functional.softplus(self.flat[hyp[0][2]:hyp[0][2] + 2]) + 1e-6
+        if not hasattr(self, "_host_hyp"):
+            self._host_hyp = {}
+        if li not in self._host_hyp:
+            self._host_hyp[li] = torch.empty(2, dtype=torch.float64).pin_memory()
+        host = self._host_hyp[li]
+        host.copy_(vals, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.flat.device))
+        return host, ev
+
+    def bind(self):
+        """Point the layers' parameters at their slices of the flat vector (idempotent)."""
+        self._push()
+
+    def step(self, grads):
+        """grads: list (per layer) of dicts of d ELBO / d constrained parameter (this rank's share)."""
+        self._store_grads(grads)
         allreduce_sum_(self.grad)                                       # the single exchange of the image-sharded step
         self.step_no += 1
         _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v), self.n,
                                       self.lr, self.b1, self.b2, self.eps, self.step_no, 1, _lib.stream()))
         self._push()
+
+
+class TrainStep(object):
+    """One optimisation step = ElboGradient + Adam with the SAME arithmetic, scheduled so that the minibatch-independent
+    tail of the step stops being serial:
+
+      * every layer's backward is split (dcgp_layer_backward_phases): the part the layer below needs (input gradient) runs
+        first, all the way down the stack; the parameter-only GEMMs (dQ, dbeta, dZ) of the upper layers are queued after it;
+      * as soon as a layer's gradients are complete, its M-only chain rule, its slice of the Adam update (and of the
+        gradient all-reduce) and its dcgp_layer_prepare for the NEXT step run on that layer's side stream, concurrently
+        with the minibatch-sized kernels still on the main stream;
+      * the kernel hyper-parameters travel by value (dcgp_layer_desc), so the host reads each layer's pair back from pinned
+        memory lazily -- right before that layer is applied in the next forward pass (layer._pending).
+
+    Parameter values after k calls are those of k x (ElboGradient, Adam.step) (tests/test_gpu_grad.py)."""
+
+    def __init__(self, model, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.model = model
+        self.eg = ElboGradient(model)
+        self.opt = Adam(model, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
+        self.opt.bind()
+
+    def _chain(self, i, wsize):
+        """Queue layer i's M-only chain rule + Adam slice on its side stream and leave the rest (hyper-parameter read-back,
+        prepare for the next step) as the layer's pending hook."""
+        model, eg, opt = self.model, self.eg, self.opt
+        layer = model.layers[i]
+        main = torch.cuda.current_stream(model.device)
+        side = eg._side[i]
+        done = torch.cuda.Event()
+        done.record(main)
+        side.wait_event(done)
+        with torch.cuda.stream(side):
+            grads = [None] * len(model.layers)
+            grads[i] = eg.bwd[i].m_only(kl_weight=1.0 / wsize)
+            host, ev = opt.step_layer(i, grads, opt.step_no)
+
+        def finish():
+            ev.synchronize()
+            v, l = host.tolist()
+            layer._base_kernel.variance, layer._base_kernel.lengthscales = v, l
+            with torch.cuda.stream(side):
+                layer.prepare()
+                layer._ready = torch.cuda.Event()
+                layer._ready.record(side)
+
+        layer._pending = finish
+
+    def __call__(self, X, Y, zs=None, n_global=None):
+        model, eg, opt = self.model, self.eg, self.opt
+        X, zs, elbo, g_mean, g_var = eg._forward(X, Y, zs, n_global)
+        Fs = model._fwd[0]
+        N, S = X.shape[0], model.num_samples
+        _, wsize = world()
+        nl = len(model.layers)
+        opt.step_no += 1
+        # input-gradient path, top to bottom (the first layer has no input gradient: its whole backward runs here)
+        for i in range(nl - 1, -1, -1):
+            first = (i == 0)
+            Xin = X if first else Fs[i - 1].reshape(S * N, -1)
+            gX = eg.bwd[i].t_sized(Xin, S if first else 1, g_mean, g_var, need_gX=not first, phases=3 if first else 1)
+            if not first:
+                g_mean, g_var = eg._sample_backward(i, gX, zs)
+        self._chain(0, wsize)
+        # parameter-only remainder of the upper layers, each followed by its own chain
+        for i in range(1, nl):
+            eg.bwd[i].t_sized_rest()
+            self._chain(i, wsize)
+        return elbo
+
+    def finish(self):
+        """Complete every pending per-layer update (host-visible parameters are then current)."""
+        for layer in self.model.layers:
+            layer._run_pending()

@@ -150,6 +150,7 @@ class _PatchGPLayer(Layer):
         self._info = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._hold = False
         self._ready = None      # CUDA event recorded after prepare() when it ran on a side stream
+        self._pending = None    # set by grad.TrainStep: finishes this layer's pipelined update + prepare() (lazy, see there)
         self.algo = None
         if q_sqrt is None:
             if not self.white:                                              # layers.py:154-158 / DS/layers.py:168-174
@@ -195,7 +196,13 @@ class _PatchGPLayer(Layer):
         if check:
             _lib.raise_if_not_pd(self._info)
 
+    def _run_pending(self):
+        if self._pending is not None:
+            fn, self._pending = self._pending, None
+            fn()
+
     def _conditional(self, X, n_rep=1, z=None):
+        self._run_pending()
         if not self._hold:
             self.prepare()
         elif self._ready is not None:
@@ -224,6 +231,7 @@ class _PatchGPLayer(Layer):
         return mean, var
 
     def KL(self):
+        self._run_pending()
         if not self._hold:
             self.prepare(check=True)
         return self._kl[0]

@@ -149,6 +149,14 @@ int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep, const void* 
                         const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
                         const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, void* ws,
                         size_t ws_bytes, void* stream);
+/* The same in two parts (same arguments and workspace for both calls):  phases & 1 = everything the input gradient gX
+ * needs (the critical path towards the layer below: dK / dd, dd . Z, col2im, Kdiag path); phases & 2 = the parameter-only
+ * remainder (dQ, dbeta, dZ), which the host may queue after the backward of the layers below so that this layer's M-only
+ * chain rule, optimiser update and next-step dcgp_layer_prepare overlap with it.  phases = 3 is dcgp_layer_backward. */
+int dcgp_layer_backward_phases(const dcgp_layer_desc* d, const void* prep, const void* apply_ws, const double* Z,
+                               const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
+                               const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw,
+                               void* ws, size_t ws_bytes, int phases, void* stream);
 /* gradient of coef * sum(varexp) w.r.t. Fmu, Fvar ([S*N, K] float32) */
 int dcgp_multiclass_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K,
                                 double epsilon, double coef, float* gmu, float* gvar, void* stream);

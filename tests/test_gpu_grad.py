@@ -122,3 +122,39 @@ def test_elbo_gradient_cfg2_shape_vs_autograd_oracle():
     for i, (got, ref) in enumerate(zip(grads, ref_grads)):
         for k, v in ref.items():
             _check("layer %d %s" % (i, k), npy(got[k]), v, floor=2e-8 * 60000.0 / N)
+
+
+@pytest.mark.parametrize("name", ["dgp2_elbo", "dgp3_elbo"])
+def test_pipelined_train_step_equals_sequential_steps(name):
+    """grad.TrainStep (split backward, per-layer Adam + prepare on side streams, lazy hyper-parameter read-back) must walk
+    the same parameter trajectory as ElboGradient + Adam.step: same ELBOs and same parameters after 4 steps."""
+    import deepcgp_b200 as D
+    if name not in golden_names("dgp"):
+        pytest.skip("golden model %s not present" % name)
+    g = load_golden(name)
+    S = int(g["S"])
+    X32 = g["X"].astype(np.float32)
+
+    def fresh():
+        layers = layers_from_golden(g)
+        model = build_model(layers, X32, g["Y"], S, float(g["num_data"]), "tc")
+        zs = [torch.as_tensor(g["z%d" % i].astype(np.float32), device=dev()) for i in range(len(layers))]
+        return model, zs
+
+    m1, zs1 = fresh()
+    eg, opt = D.ElboGradient(m1), D.Adam(m1, lr=0.01)
+    e1 = []
+    for _ in range(4):
+        elbo, grads = eg(X32, g["Y"], zs=zs1)
+        e1.append(float(elbo.item()))
+        opt.step(grads)
+    m2, zs2 = fresh()
+    step = D.TrainStep(m2, lr=0.01)
+    e2 = [float(step(X32, g["Y"], zs=zs2).item()) for _ in range(4)]
+    step.finish()
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(e2, e1, rtol=1e-7)
+    np.testing.assert_allclose(npy(step.opt.flat), npy(opt.flat), rtol=1e-6, atol=1e-9)
+    for l1, l2 in zip(m1.layers, m2.layers):
+        assert abs(l1._base_kernel.variance - l2._base_kernel.variance) <= 1e-9 * abs(l1._base_kernel.variance)
+        assert abs(l1._base_kernel.lengthscales - l2._base_kernel.lengthscales) <= 1e-9 * abs(l1._base_kernel.lengthscales)
