@@ -155,24 +155,15 @@ int rbf_sym_f64(const double* Z, int M, int L, double variance, double lengthsca
 }
 
 // ------------------------------------------------------------------------------------------ Cholesky
-// Diagonal block: factor an nb<=64 block held in shared memory and also form its inverse (used for the panel
-// solve and as the seed of the triangular inverse).  Padding rows/cols behave as identity.
+// Diagonal block: factor an nb<=64 block held in shared memory `s` (padding rows/cols = identity), write it back to A,
+// and form its inverse in `x` -> invD (used for the panel solve and as the seed of the triangular inverse).
 // Blocked inside the CTA (16-wide panels: warp-level factor, row-parallel panel solve, rank-16 trailing update), then
 // the inverse by recursive doubling on 16 -> 32 -> 64 blocks: a dozen block barriers instead of ~200.
-__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int lda, int j0, int nb,
-                                                         double* __restrict__ invD, int* __restrict__ info) {
-  extern __shared__ double dyn_smem[];
-  double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
-  double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
-  double (*tm)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + 2 * NB * (NB + 1));
+// Must be called by all 256 threads of the CTA; `s` must be fully populated and visible (barrier) on entry.
+__device__ void factor_diag_smem(double (*s)[NB + 1], double (*x)[NB + 1], double (*tm)[NB + 1], double* __restrict__ A,
+                                 int lda, int j0, int nb, double* __restrict__ invD, int* __restrict__ info) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e >> 6, j = e & 63;
-    double v = (i == j) ? 1.0 : 0.0;
-    if (i < nb && j < nb) v = (j <= i) ? A[(long long)(j0 + i) * lda + j0 + j] : 0.0;
-    s[i][j] = v;
-    x[i][j] = 0.0;
-  }
+  for (int e = tid; e < NB * NB; e += 256) x[e >> 6][e & 63] = 0.0;
   __syncthreads();
   for (int k0 = 0; k0 < NB; k0 += 16) {
     if (warp == 0) {   // 16x16 diagonal block, one warp
@@ -267,68 +258,158 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
   for (int e = tid; e < NB * NB; e += 256) invD[e] = x[e >> 6][e & 63];
 }
 
-// Panel solve: A[i, j0:j0+nb] <- A[i, j0:j0+nb] * inv(Ljj)^T for rows i >= j0+nb, 64 rows per CTA.
-__global__ void __launch_bounds__(256) trsm_panel_kernel(double* __restrict__ A, int lda, int M, int j0, int nb,
-                                                         const double* __restrict__ invD) {
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int lda, int j0, int nb,
+                                                         double* __restrict__ invD, int* __restrict__ info) {
   extern __shared__ double dyn_smem[];
-  double (*P)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
-  double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
-  const int r0 = j0 + nb + blockIdx.x * NB;
-  const int tid = threadIdx.x;
+  double (*s)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
+  double (*x)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
+  double (*tm)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + 2 * NB * (NB + 1));
+  for (int e = threadIdx.x; e < NB * NB; e += 256) {
+    const int i = e >> 6, j = e & 63;
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < nb && j < nb) v = (j <= i) ? A[(long long)(j0 + i) * lda + j0 + j] : 0.0;
+    s[i][j] = v;
+  }
+  __syncthreads();
+  factor_diag_smem(s, x, tm, A, lda, j0, nb, invD, info);
+}
+
+// One launch per 64-column panel of the right-looking factorisation (after the diagonal block j has been factored and
+// inverted): CTA (bi, bk), bi >= bk >= 1 (block offsets past panel j), owns the trailing tile A[j+bi, j+bk] and does
+//   X_i = P_i inv(L_jj)^T, X_k = P_k inv(L_jj)^T      (panel solve, recomputed per tile: 2 x 64^3 flops, no extra launch)
+//   A[j+bi, j+bk] -= X_i X_k^T                         (rank-64 update)
+// the bk == 1 column of CTAs also stores X_i as the final panel of L (transposed, in the upper triangle), and CTA (1, 1)
+// goes straight on to factor and invert
+// the NEXT diagonal block (look-ahead), so the whole factorisation is nblk launches with no separate diag/solve kernels.
+__global__ void __launch_bounds__(256) chol_step_kernel(double* __restrict__ A, int lda, int M, int j0,
+                                                        const double* __restrict__ invD, double* __restrict__ invD_next,
+                                                        int* __restrict__ info) {
+  extern __shared__ double dyn_smem[];
+  double (*Pi)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
+  double (*Pk)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
+  double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + 2 * NB * (NB + 1));
+  // linear tile index -> (bi, bk), bi >= bk >= 1
+  int bi = 1, t = blockIdx.x;
+  while (t >= bi) { t -= bi; ++bi; }
+  const int bk = t + 1;
+  const int ri0 = j0 + bi * NB, rk0 = j0 + bk * NB;          // first rows of blocks i and k (rk0 is also the tile's column origin)
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const bool diag = (bi == bk);
   for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, j = e % NB;
-    P[i][j] = (r0 + i < M && j < nb) ? A[(long long)(r0 + i) * lda + j0 + j] : 0.0;
+    const int i = e >> 6, j = e & 63;
+    Pi[i][j] = (ri0 + i < M) ? A[(long long)(ri0 + i) * lda + j0 + j] : 0.0;
+    if (!diag) Pk[i][j] = (rk0 + i < M) ? A[(long long)(rk0 + i) * lda + j0 + j] : 0.0;
     D[i][j] = invD[e];
   }
   __syncthreads();
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, c = e % NB;
-    if (r0 + i < M && c < nb) {
-      double acc = 0.0;
-      for (int k = 0; k <= c; ++k) acc = fma(P[i][k], D[c][k], acc);  // inv(Ljj) is lower: D[c][k], k <= c
-      A[(long long)(r0 + i) * lda + j0 + c] = acc;
-    }
+  // panel solve through the inverse of the diagonal block: X[r][c] = sum_{k <= c} P[r][k] * D[c][k]; 4x4 per thread
+  double xi[4][4], xk[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { xi[u][v] = 0.0; xk[u][v] = 0.0; }
+  for (int k = 0; k < tx * 4 + 4; ++k) {
+    double d[4], a[4], b[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) d[v] = (k <= tx * 4 + v) ? D[tx * 4 + v][k] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = Pi[ty * 4 + u][k]; b[u] = diag ? 0.0 : Pk[ty * 4 + u][k]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { xi[u][v] = fma(a[u], d[v], xi[u][v]); xk[u][v] = fma(b[u], d[v], xk[u][v]); }
   }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      Pi[ty * 4 + u][tx * 4 + v] = xi[u][v];
+      if (!diag) Pk[ty * 4 + u][tx * 4 + v] = xk[u][v];
+      // final L panel: parked TRANSPOSED in the (otherwise unused) upper triangle -- other CTAs of this launch still read
+      // the raw panel in place; lower_from_upper_kernel moves it home at the end
+      if (bk == 1 && ri0 + ty * 4 + u < M) A[(long long)(j0 + tx * 4 + v) * lda + ri0 + ty * 4 + u] = xi[u][v];
+    }
+  __syncthreads();
+  double (*Xk)[NB + 1] = diag ? Pi : Pk;
+  // rank-64 update of this tile: rows ty*4.., cols tx*4..
+  double acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int gi = ri0 + ty * 4 + u, gj = rk0 + tx * 4 + v;
+      acc[u][v] = (gi < M && gj < M) ? A[(long long)gi * lda + gj] : 0.0;
+    }
+#pragma unroll 4
+  for (int k = 0; k < NB; ++k) {
+    double a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = Pi[ty * 4 + u][k]; b[u] = Xk[tx * 4 + u][k]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = fma(-a[u], b[v], acc[u][v]);
+  }
+  if (!(diag && bi == 1)) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int gi = ri0 + ty * 4 + u, gj = rk0 + tx * 4 + v;
+        if (gi < M && gj < M) A[(long long)gi * lda + gj] = acc[u][v];
+      }
+    return;
+  }
+  // CTA (1, 1): the updated tile is the next diagonal block -> factor + invert it right here (look-ahead)
+  __syncthreads();                                   // everyone is done reading Pi / D
+  const int jn = j0 + NB, nbn = (M - jn < NB) ? (M - jn) : NB;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = ty * 4 + u, j = tx * 4 + v;
+      double val = (i == j) ? 1.0 : 0.0;
+      if (i < nbn && j < nbn) val = (j <= i) ? acc[u][v] : 0.0;
+      Pi[i][j] = val;
+    }
+  __syncthreads();
+  factor_diag_smem(Pi, Pk, D, A, lda, jn, nbn, invD_next, info);
 }
 
-__global__ void zero_upper_kernel(double* __restrict__ A, int lda, int M) {
+// Off-diagonal blocks of L were parked transposed in the upper triangle (chol_step_kernel): move them home, zero the upper
+// triangle.  One thread per (i, j), j < i: it alone touches A[i][j] and A[j][i].
+__global__ void lower_from_upper_kernel(double* __restrict__ A, int lda, int M) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-  if (i < M && j < M && j > i) A[(long long)i * lda + j] = 0.0;
+  if (i < M && j < i) {
+    if (i / NB != j / NB) A[(long long)i * lda + j] = A[(long long)j * lda + i];
+    A[(long long)j * lda + i] = 0.0;
+  }
 }
 
 size_t potrf_ws_bytes(int M) { return (size_t)ceil_div(M, NB) * NB * NB * sizeof(double); }
 
 constexpr int kDiagSmem = 3 * NB * (NB + 1) * sizeof(double);
 
-// Right-looking blocked Cholesky: per 64-column panel (1) factor + invert the diagonal block in one CTA, (2) solve the
-// panel below it, (3) rank-64 update of the trailing lower triangle -- a wide, shallow GEMM (k = 64) that fills the machine,
-// where a left-looking update would be a narrow GEMM with a long sequential k loop.
+// Right-looking blocked Cholesky, ONE launch per 64-column panel (chol_step_kernel): panel solve, rank-64 update of the
+// trailing lower triangle (a wide, shallow update that fills the machine, where a left-looking update would be a narrow
+// GEMM with a long sequential k loop) and the factor + inverse of the next diagonal block.
 int potrf_f64(double* A, int lda, int M, double* invD, int* info, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
-    cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
+    cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDiagSmem);
     attr_set = true;
   }
   const int nblk = ceil_div(M, NB);
-  for (int jb = 0; jb < nblk; ++jb) {
-    const int j0 = jb * NB, nb = (M - j0 < NB) ? (M - j0) : NB;
-    potrf_diag_kernel<<<1, 256, kDiagSmem, st>>>(A, lda, j0, nb, invD + (size_t)jb * NB * NB, info);
-    const int rows_below = M - j0 - nb;
-    if (rows_below > 0) {
-      trsm_panel_kernel<<<ceil_div(rows_below, NB), 256, kDiagSmem, st>>>(A, lda, M, j0, nb, invD + (size_t)jb * NB * NB);
-      GemmF64 g{};   // A22 -= P P^T  (lower tiles only)
-      g.m = g.n = rows_below; g.k = nb;
-      g.A = A + (long long)(j0 + nb) * lda + j0; g.lda = lda; g.transA = 0;
-      g.B = g.A; g.ldb = lda; g.transB = 1;
-      g.C = A + (long long)(j0 + nb) * lda + (j0 + nb); g.ldc = lda;
-      g.alpha = -1.0; g.beta = 1.0; g.batch = 1; g.lowerC = 1;
-      int rc = gemm_f64(g, st);
-      if (rc) return rc;
-    }
+  potrf_diag_kernel<<<1, 256, kDiagSmem, st>>>(A, lda, 0, M < NB ? M : NB, invD, info);
+  for (int jb = 0; jb + 1 < nblk; ++jb) {            // panel jb: solve + trailing update + factor of diagonal block jb+1
+    const int nt = nblk - 1 - jb;                    // trailing blocks
+    chol_step_kernel<<<nt * (nt + 1) / 2, 256, kDiagSmem, st>>>(A, lda, M, jb * NB, invD + (size_t)jb * NB * NB,
+                                                                invD + (size_t)(jb + 1) * NB * NB, info);
   }
-  zero_upper_kernel<<<dim3(ceil_div(M, 256), M), 256, 0, st>>>(A, lda, M);
-  return check_launch("potrf_f64", 2 * nblk);   // nblk diag + (nblk-1) panel solves + zero_upper
+  lower_from_upper_kernel<<<dim3(ceil_div(M, 256), M), 256, 0, st>>>(A, lda, M);
+  return check_launch("potrf_f64", nblk + 1);
 }
 
 // ------------------------------------------------------------------------------------------ L^-1

@@ -75,12 +75,14 @@ class LayerBackward(object):
             _lib.ptr(self.gw) if layer._kind == _lib.LAYER_SVGP_CONV else None, _lib.ptr(ws), ws.numel(), phases,
             _lib.stream()))
 
-    def m_only(self, kl_weight=1.0):
+    def m_only(self, kl_weight=1.0, hyp=None):
         """Chain rule through the minibatch-independent operands; returns d ELBO / d{Z, variance, lengthscale, q_mu,
-        q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that summing over ranks counts the KL once."""
+        q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that summing over ranks counts the KL once.
+        `hyp` (optional): device tensor [variance, lengthscale] to use instead of the host floats -- keeps the whole chain
+        free of host values so that it can be captured in a CUDA graph (TrainStep)."""
         if self.layer.white:
             return self._m_only_autograd(kl_weight)
-        return self._m_only_closed_form(kl_weight)
+        return self._m_only_closed_form(kl_weight, hyp)
 
     @staticmethod
     def _rbf_parts(Z, var, ls):
@@ -116,7 +118,7 @@ class LayerBackward(object):
         return Kinv, Lpinv
 
     @torch.no_grad()
-    def _m_only_closed_form(self, kl_weight):
+    def _m_only_closed_form(self, kl_weight, hyp=None):
         """Non-whitened case, written out as ~15 batched float64 GEMMs (no autograd graph, no triangular solves):
              Q_0 = Kinv, Q_r = B_r B_r^T with B_r = Kinv L_r, beta = Kinv q_mu       (Kinv = Kuu^-1)
              KL  = 1/2 [q_mu^T Kp^-1 q_mu - MR - sum log diag(L_r)^2 + sum <L_r, Kp^-1 L_r> + R log|Kp|]"""
@@ -126,9 +128,11 @@ class LayerBackward(object):
         gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
         gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
         Z = layer.feature.Z.to(torch.float64)
-        var, ls = float(layer._base_kernel.variance), float(layer._base_kernel.lengthscales)
+        if hyp is None:
+            var, ls = float(layer._base_kernel.variance), float(layer._base_kernel.lengthscales)
+        else:
+            var, ls = hyp[0], hyp[1]
         q_mu, Lq = layer.q_mu, torch.tril(layer.q_sqrt)
-        eye = torch.eye(M, dtype=torch.float64, device=dev)
         Kn, D = self._rbf_parts(Z, var, ls)
         # Kuu^-1 and the prior's Lp^-1 were already formed (float64) by this step's dcgp_layer_prepare: re-use them
         Kinv, Lpinv = self._forward_inverses()
@@ -363,18 +367,24 @@ class Adam(object):
         offs = [(s[2], s[2] + s[3]) for s in self.slots if s[0] == li]
         return min(o[0] for o in offs), max(o[1] for o in offs)
 
+    def hyp_slice(self, li):
+        """The layer's unconstrained (variance, lengthscale) pair inside the flat vector."""
+        hyp = [s for s in self.slots if s[0] == li and s[1] in ("variance", "lengthscale")]
+        assert hyp[0][1] == "variance" and hyp[1][2] == hyp[0][2] + 1
+        return self.flat[hyp[0][2]:hyp[0][2] + 2]
+
     def step_layer(self, li, grads, step_no):
         """Adam update of layer li's slice on the CURRENT stream; returns (pinned host tensor, event) of the layer's
-        constrained (variance, lengthscale) -- they travel by value in dcgp_layer_desc, so the host needs them back."""
-        self._store_grads(grads, li)
+        constrained (variance, lengthscale) -- they travel by value in dcgp_layer_desc, so the host needs them back.
+        grads=None: the layer's slice of self.grad has already been filled (captured graph)."""
+        if grads is not None:
+            self._store_grads(grads, li)
         lo, hi = self.layer_range(li)
         allreduce_sum_(self.grad[lo:hi])
         _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat[lo:hi]), _lib.ptr(self.grad[lo:hi]), _lib.ptr(self.m[lo:hi]),
                                       _lib.ptr(self.v[lo:hi]), hi - lo, self.lr, self.b1, self.b2, self.eps, step_no, 1,
                                       _lib.stream()))
-        hyp = [s for s in self.slots if s[0] == li and s[1] in ("variance", "lengthscale")]
-        assert hyp[0][1] == "variance" and hyp[1][2] == hyp[0][2] + 1
-        vals = torch.nn.functional.softplus(self.flat[hyp[0][2]:hyp[0][2] + 2]) + 1e-6
+        vals = torch.nn.functional.softplus(self.hyp_slice(li)) + 1e-6
         if not hasattr(self, "_host_hyp"):
             self._host_hyp = {}
         if li not in self._host_hyp:
@@ -413,11 +423,42 @@ class TrainStep(object):
 
     Parameter values after k calls are those of k x (ElboGradient, Adam.step) (tests/test_gpu_grad.py)."""
 
-    def __init__(self, model, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+    GRAPH_AFTER = 2     # eager calls before a layer's M-only chain is captured in a CUDA graph
+
+    def __init__(self, model, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, use_graphs=True):
         self.model = model
         self.eg = ElboGradient(model)
         self.opt = Adam(model, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
         self.opt.bind()
+        self.use_graphs = use_graphs
+        self._graphs = [None] * len(model.layers)
+        self._calls = [0] * len(model.layers)
+
+    def _m_only_to_grad(self, i, wsize):
+        """Layer i's M-only chain rule, results stored in its slice of opt.grad (current stream).  ~60 small float64 torch
+        ops with fixed shapes and pointers and no host values: after GRAPH_AFTER eager calls they are replayed as ONE CUDA
+        graph launch (the chain is otherwise bound by host launch overhead)."""
+        eg, opt = self.eg, self.opt
+        layer = self.model.layers[i]
+
+        def run():
+            hyp = torch.nn.functional.softplus(opt.hyp_slice(i)) + 1e-6       # == the values the host holds
+            grads = [None] * len(self.model.layers)
+            grads[i] = eg.bwd[i].m_only(kl_weight=1.0 / wsize, hyp=hyp)
+            opt._store_grads(grads, i)
+
+        if not self.use_graphs or layer.white:
+            return run()
+        if self._graphs[i] is not None:
+            return self._graphs[i].replay()
+        self._calls[i] += 1
+        if self._calls[i] <= self.GRAPH_AFTER:
+            return run()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=torch.cuda.current_stream(self.model.device), capture_error_mode="thread_local"):
+            run()
+        self._graphs[i] = g
+        g.replay()
 
     def _chain(self, i, wsize):
         """Queue layer i's M-only chain rule + Adam slice on its side stream and leave the rest (hyper-parameter read-back,
@@ -430,9 +471,8 @@ class TrainStep(object):
         done.record(main)
         side.wait_event(done)
         with torch.cuda.stream(side):
-            grads = [None] * len(model.layers)
-            grads[i] = eg.bwd[i].m_only(kl_weight=1.0 / wsize)
-            host, ev = opt.step_layer(i, grads, opt.step_no)
+            self._m_only_to_grad(i, wsize)
+            host, ev = opt.step_layer(i, None, opt.step_no)
 
         def finish():
             ev.synchronize()
