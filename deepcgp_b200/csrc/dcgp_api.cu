@@ -390,6 +390,15 @@ int dcgp_prepare_workspace_layout(const dcgp_layer_desc* d, size_t* off_kinv, si
   return DCGP_OK;
 }
 
+int dcgp_prepare_layout(const dcgp_layer_desc* d, size_t* off_b32, int* ld_b) {
+  if (check_desc(d)) return DCGP_ERR_ARG;
+  char* const fake = (char*)(uintptr_t)(1u << 20);
+  Prep p = carve_prep(d, fake);
+  if (off_b32) *off_b32 = (size_t)((char*)p.tc.Br32 - fake);
+  if (ld_b) *ld_b = p.Mp;
+  return DCGP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- layer apply
 struct ApplyWork {
   float *Kt, *acc, *mean_t, *Kzx, *kdiag;

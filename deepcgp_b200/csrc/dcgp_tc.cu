@@ -774,6 +774,7 @@ void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   t.BRh = c.take((size_t)R * Mp * Mp * 2);
   t.BRl = c.take((size_t)R * Mp * Mp * 2);
   t.Br32 = (float*)c.take((size_t)R * Mp * Mp * 4);
+  t.Qr32 = (float*)c.take((size_t)R * Mp * Mp * 4);
   t.QBh = c.take(((size_t)R * Mp + 256) * Mp * 2);
   t.QBl = c.take(((size_t)R * Mp + 256) * Mp * 2);
   t.beta32 = (float*)c.take((size_t)Mp * 64 * 4);
@@ -869,12 +870,13 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
     b2.Bh = t.BRh; b2.Bl = t.BRl; b2.b_rows_total = (long long)R * Mp; b2.b_batch_rows = Mp;
     b2.batch = R; b2.m = M; b2.n = M; b2.m_pad = Mp; b2.n_pad = Mp; b2.k_pad = Mp;
     b2.a_scal = t.scal + 14; b2.b_scal = t.scal + 14;
-    b2.C = t.Br32; b2.c_batch_stride = (long long)Mp * Mp; b2.ldc = Mp;     // Br32 now holds Q_r
+    b2.C = t.Qr32; b2.c_batch_stride = (long long)Mp * Mp; b2.ldc = Mp;     // Br32 keeps B_r for the M-only chain rule
+    if (M != Mp) cudaMemsetAsync(t.Qr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
     if ((rc = tc_gemm(b2, st))) return rc;
-    if ((rc = maxabs_f32(t.Br32, (long long)R * Mp * Mp, t.mx + 5, st))) return rc;
+    if ((rc = maxabs_f32(t.Qr32, (long long)R * Mp * Mp, t.mx + 5, st))) return rc;
     if ((rc = maxabs_f64(Kinv, M, M, M, 0, t.mx + 5, st))) return rc;
     if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 6, st))) return rc;
-    pack_qp_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Kinv, t.Br32, beta, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl,
+    pack_qp_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Kinv, t.Qr32, beta, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl,
                                                       t.beta32, t.scal + 16, (__half*)t.BTh, (__half*)t.BTl);
     if ((rc = check_launch("tc_build_backward_operands", 3))) return rc;
   }

@@ -21,7 +21,8 @@ struct TcPrep {
   float* Wr32;       // [R*Mp, Mp] fp32 W_r (tensor-core product)
   // ---- operands of the backward pass
   void *BRh, *BRl;   // [R*Mp, Mp]   B_r = W_r^T = G L_r
-  float* Br32;       // [R*Mp, Mp]   (also reused for Q_r = B_r B_r^T)
+  float* Br32;       // [R*Mp, Mp]   B_r in fp32 (read back by the host's M-only chain rule, dcgp_prepare_layout)
+  float* Qr32;       // [R*Mp, Mp]   Q_r = B_r B_r^T
   void *QBh, *QBl;   // [R*Mp + 256, Mp]  QP_r = 2 (Q_r - Q_0) stacked over r = 1..R (B operand of the dK GEMM), zero padded
   float* beta32;     // [Mp, 64]     beta[m, r] (fp32), zero padded
   void *ZTh, *ZTl;   // [LpT, Mp]    bf16 planes of (Z / lengthscale)^T * kXScale; row L = kXScale (ones row: DDZ[:, L] = row sums of dd)

@@ -117,6 +117,17 @@ class LayerBackward(object):
         Lpinv = ws[op:op + ld * ld * 8].view(torch.float64).view(ld, ld)[:M, :M]
         return Kinv, Lpinv
 
+    def _forward_B(self):
+        """View of B_r = Kuu^-1 L_r (float32 [R, M, M], tensor-core product of this step's dcgp_layer_prepare)."""
+        import ctypes as C
+        layer, M, R = self.layer, self.M, self.R
+        if getattr(self, "_boff", None) is None:
+            ob, ld = C.c_size_t(), C.c_int()
+            _lib.check(_lib.lib.dcgp_prepare_layout(layer._desc(), C.byref(ob), C.byref(ld)))
+            self._boff = (ob.value, ld.value)
+        ob, ld = self._boff
+        return layer._prep[ob:ob + R * ld * ld * 4].view(torch.float32).view(R, ld, ld)[:, :M, :M]
+
     @torch.no_grad()
     def _m_only_closed_form(self, kl_weight, hyp=None):
         """Non-whitened case, written out as ~15 batched float64 GEMMs (no autograd graph, no triangular solves):
@@ -136,7 +147,10 @@ class LayerBackward(object):
         Kn, D = self._rbf_parts(Z, var, ls)
         # Kuu^-1 and the prior's Lp^-1 were already formed (float64) by this step's dcgp_layer_prepare: re-use them
         Kinv, Lpinv = self._forward_inverses()
-        B = Kinv @ Lq                                                    # [R,M,M]
+        if layer._algo() == _lib.ALGO_TC:
+            B = self._forward_B().to(torch.float64)                      # [R,M,M] = Kinv @ Lq, already formed this step
+        else:
+            B = Kinv @ Lq
         U = (gQ[1:] + gQ[1:].transpose(1, 2)) @ B                        # d/dB_r
         gLq = Kinv @ U                                                   # d/dL_r (through B_r)
         GK = gQ[0] + torch.einsum("rij,rkj->ik", U, Lq) + gbeta @ q_mu.T # d/dKinv
@@ -226,7 +240,10 @@ class ElboGradient(object):
         _lib.check(_lib.lib.dcgp_multiclass_varexp_grad(_lib.ptr(Fm), _lib.ptr(Fv), _lib.ptr(Yd), S, N, K, lik.epsilon, coef,
                                                         _lib.ptr(g_mean), _lib.ptr(g_var), _lib.stream()))
         if self._side is None:
-            self._side = [torch.cuda.Stream(device=model.device) for _ in model.layers]
+            # chain streams outrank the main stream (their kernels are small and latency-critical); the first layer's chain
+            # -- the one the next forward pass waits for first -- outranks the others
+            # (CUDA clamps priorities to the supported range; lower = more urgent)
+            self._side = [torch.cuda.Stream(device=model.device, priority=-2 if i == 0 else -1) for i in range(len(model.layers))]
         return X, zs, elbo, g_mean, g_var
 
     def _sample_backward(self, i, gX, zs):

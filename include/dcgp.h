@@ -115,6 +115,9 @@ size_t dcgp_prepare_workspace_bytes(const dcgp_layer_desc* d);
 /* Byte offsets, inside the workspace of the last dcgp_layer_prepare (algo = DCGP_ALGO_TC), of float64 results the host-side
  * chain rule re-uses: Kuu^-1 [M,M] (ld M), Lm^-1 and the prior's Lp^-1 (lower triangular, ld = *ld_inv >= M). */
 int dcgp_prepare_workspace_layout(const dcgp_layer_desc* d, size_t* off_kinv, size_t* off_linv, size_t* off_lpinv, int* ld_inv);
+/* Offset (bytes) inside the `prep` buffer of B_r = G L_r as float32 [R, ld_b, ld_b] (tensor-core path, non-whitened:
+ * G = Kuu^-1), left there by dcgp_layer_prepare for the host-side M-only chain rule. */
+int dcgp_prepare_layout(const dcgp_layer_desc* d, size_t* off_b32, int* ld_b);
 int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
                        const double* q_sqrt, int algo, void* prep, double* kl, void* ws, size_t ws_bytes,
                        int* info, void* stream);
