@@ -162,31 +162,37 @@ int rbf_sym_f64(const double* Z, int M, int L, double variance, double lengthsca
 // Must be called by all 256 threads of the CTA; `s` must be fully populated and visible (barrier) on entry.
 __device__ void factor_diag_smem(double (*s)[NB + 1], double (*x)[NB + 1], double (*tm)[NB + 1], double* __restrict__ A,
                                  int lda, int j0, int nb, double* __restrict__ invD, int* __restrict__ info) {
+  __shared__ double invd[NB];                       // 1 / diag(L): every later division becomes a multiplication
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int e = tid; e < NB * NB; e += 256) x[e >> 6][e & 63] = 0.0;
   __syncthreads();
   for (int k0 = 0; k0 < NB; k0 += 16) {
-    if (warp == 0) {   // 16x16 diagonal block, one warp
-      for (int k = 0; k < 16; ++k) {
-        if (lane == 0) {
-          const double p = s[k0 + k][k0 + k];
-          if (!(p > 0.0)) {
-            atomicCAS(info, 0, j0 + k0 + k + 1);
-            s[k0 + k][k0 + k] = nan("");
-          } else {
-            s[k0 + k][k0 + k] = sqrt(p);
-          }
-        }
-        __syncwarp();
-        const double dkk = s[k0 + k][k0 + k];
-        if (lane > k && lane < 16) s[k0 + lane][k0 + k] /= dkk;
-        __syncwarp();
+    if (warp == 0) {
+      // 16x16 diagonal block in REGISTERS: lane i (< 16) owns row i; column k is broadcast by shuffles, the pivot's
+      // reciprocal square root replaces sqrt + divide.  Fully unrolled so that a[] stays in registers.
+      const int i = lane & 15;
+      double a[16];
 #pragma unroll
-        for (int e = lane; e < 256; e += 32) {
-          const int i = e >> 4, j = e & 15;
-          if (j > k && j <= i) s[k0 + i][k0 + j] -= s[k0 + i][k0 + k] * s[k0 + j][k0 + k];
+      for (int j = 0; j < 16; ++j) a[j] = s[k0 + i][k0 + j];
+      int bad = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const double p = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(p > 0.0) && !bad) bad = k0 + k + 1;
+        const double rs = rsqrt(p);
+        a[k] = (i == k) ? p * rs : a[k] * rs;       // rows below the pivot: l_ik = a_ik / l_kk
+        if (i == k) invd[k0 + k] = rs;
+#pragma unroll
+        for (int j = k + 1; j < 16; ++j) {
+          const double ljk = __shfl_sync(0xffffffffu, a[k], j);
+          a[j] = fma(-a[k], ljk, a[j]);             // meaningful for i >= j
         }
-        __syncwarp();
+      }
+      if (bad && lane == 0) atomicCAS(info, 0, j0 + bad);
+      if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j <= i) s[k0 + i][k0 + j] = a[j];
       }
     }
     __syncthreads();
@@ -201,7 +207,7 @@ __device__ void factor_diag_smem(double (*s)[NB + 1], double (*x)[NB + 1], doubl
         double v = r[j];
 #pragma unroll
         for (int l = 0; l < j; ++l) v = fma(-r[l], s[k0 + j][k0 + l], v);
-        r[j] = v / s[k0 + j][k0 + j];
+        r[j] = v * invd[k0 + j];
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) s[i][k0 + j] = r[j];
@@ -227,11 +233,11 @@ __device__ void factor_diag_smem(double (*s)[NB + 1], double (*x)[NB + 1], doubl
   // ---- inverse: 16x16 diagonal blocks by forward substitution (one column per thread) ...
   if (tid < NB) {
     const int b0 = (tid >> 4) << 4, c = tid;
-    x[c][c] = 1.0 / s[c][c];
+    x[c][c] = invd[c];
     for (int i = c + 1; i < b0 + 16; ++i) {
       double acc = 0.0;
       for (int k = c; k < i; ++k) acc = fma(s[i][k], x[k][c], acc);
-      x[i][c] = -acc / s[i][i];
+      x[i][c] = -acc * invd[i];
     }
   }
   __syncthreads();
@@ -302,18 +308,21 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double* __restrict__ A, 
     D[i][j] = invD[e];
   }
   __syncthreads();
-  // panel solve through the inverse of the diagonal block: X[r][c] = sum_{k <= c} P[r][k] * D[c][k]; 4x4 per thread
+  // panel solve through the inverse of the diagonal block: X[r][c] = sum_k P[r][k] * D[c][k] (D lower triangular, stored
+  // with zeros above the diagonal).  4x4 outputs per thread at rows ty + 16u, cols tx + 16v: the 16 lanes that differ in
+  // tx read 16 consecutive shared-memory words (no bank conflicts), the two ty values of a warp are broadcasts.
   double xi[4][4], xk[4][4];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 4; ++v) { xi[u][v] = 0.0; xk[u][v] = 0.0; }
-  for (int k = 0; k < tx * 4 + 4; ++k) {
+#pragma unroll 2
+  for (int k = 0; k < NB; ++k) {
     double d[4], a[4], b[4];
 #pragma unroll
-    for (int v = 0; v < 4; ++v) d[v] = (k <= tx * 4 + v) ? D[tx * 4 + v][k] : 0.0;
+    for (int v = 0; v < 4; ++v) d[v] = D[tx + 16 * v][k];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { a[u] = Pi[ty * 4 + u][k]; b[u] = diag ? 0.0 : Pk[ty * 4 + u][k]; }
+    for (int u = 0; u < 4; ++u) { a[u] = Pi[ty + 16 * u][k]; b[u] = diag ? 0.0 : Pk[ty + 16 * u][k]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -324,28 +333,28 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double* __restrict__ A, 
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      Pi[ty * 4 + u][tx * 4 + v] = xi[u][v];
-      if (!diag) Pk[ty * 4 + u][tx * 4 + v] = xk[u][v];
+      Pi[ty + 16 * u][tx + 16 * v] = xi[u][v];
+      if (!diag) Pk[ty + 16 * u][tx + 16 * v] = xk[u][v];
       // final L panel: parked TRANSPOSED in the (otherwise unused) upper triangle -- other CTAs of this launch still read
       // the raw panel in place; lower_from_upper_kernel moves it home at the end
-      if (bk == 1 && ri0 + ty * 4 + u < M) A[(long long)(j0 + tx * 4 + v) * lda + ri0 + ty * 4 + u] = xi[u][v];
+      if (bk == 1 && ri0 + ty + 16 * u < M) A[(long long)(j0 + tx + 16 * v) * lda + ri0 + ty + 16 * u] = xi[u][v];
     }
   __syncthreads();
   double (*Xk)[NB + 1] = diag ? Pi : Pk;
-  // rank-64 update of this tile: rows ty*4.., cols tx*4..
+  // rank-64 update of this tile
   double acc[4][4];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      const int gi = ri0 + ty * 4 + u, gj = rk0 + tx * 4 + v;
+      const int gi = ri0 + ty + 16 * u, gj = rk0 + tx + 16 * v;
       acc[u][v] = (gi < M && gj < M) ? A[(long long)gi * lda + gj] : 0.0;
     }
 #pragma unroll 4
   for (int k = 0; k < NB; ++k) {
     double a[4], b[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { a[u] = Pi[ty * 4 + u][k]; b[u] = Xk[tx * 4 + u][k]; }
+    for (int u = 0; u < 4; ++u) { a[u] = Pi[ty + 16 * u][k]; b[u] = Xk[tx + 16 * u][k]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double* __restrict__ A, 
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const int gi = ri0 + ty * 4 + u, gj = rk0 + tx * 4 + v;
+        const int gi = ri0 + ty + 16 * u, gj = rk0 + tx + 16 * v;
         if (gi < M && gj < M) A[(long long)gi * lda + gj] = acc[u][v];
       }
     return;
@@ -368,7 +377,7 @@ __global__ void __launch_bounds__(256) chol_step_kernel(double* __restrict__ A, 
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      const int i = ty * 4 + u, j = tx * 4 + v;
+      const int i = ty + 16 * u, j = tx + 16 * v;
       double val = (i == j) ? 1.0 : 0.0;
       if (i < nbn && j < nbn) val = (j <= i) ? acc[u][v] : 0.0;
       Pi[i][j] = val;
