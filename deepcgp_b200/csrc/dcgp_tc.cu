@@ -98,6 +98,22 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Same load without the wait: lets the next chunk's TMEM read overlap the current chunk's arithmetic (tmem_ld_wait() before
+// the registers are used).
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, rows of 128 bytes (64 fp16), 8-row groups 1024 B apart
 // (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64).
@@ -925,13 +941,23 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
-  float* xx_s = (float*)(tmem_base_smem + 4);     // [4 tiles][128] squared norms of the tile's patches (ring over tiles)
+  float* xx_s = (float*)(tmem_base_smem + 4);     // [4 tiles][128] exponent offsets of the tile's patches (ring over tiles)
   int* off_s = (int*)(xx_s + 4 * 2 * kBM);        // [nkb*64] image offset of patch element l (im2col index math, once per CTA)
+  float* zc_s = (float*)(off_s + p.nkb * kBK);    // [Mp] per-column exponent offset log2(ks) - 0.5 log2(e) |zs_m|^2 (-inf: padding)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = p.v.L;
+  // k = ks * exp(-0.5 (xx + zz - 2 D)) = exp2(c2 * acc + zc[m] + xc[t]) with acc = kXScale^2 * D from the tensor core:
+  // one FFMA + one FADD + one MUFU.EX2 per element, and the padding (m >= M, t >= T) falls out as exp2(-inf) = 0.
+  constexpr float kLog2e = 1.4426950408889634f;
+  const float c2 = kLog2e / (kXScale * kXScale);
 
   for (int l = threadIdx.x; l < p.nkb * kBK; l += kKufThreads) off_s[l] = (l < L) ? p.v.elem_off(l) : 0;
+  {
+    const float lks = log2f(p.kscal[0] * p.variance);
+    for (int m = threadIdx.x; m < p.Mp; m += kKufThreads)
+      zc_s[m] = (m < p.M) ? fmaf(-0.5f * kLog2e, p.zz[m], lks) : -INFINITY;
+  }
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmZ_hi); tma_prefetch_desc(&tmZ_lo);
     for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], kKufGatherWarps + 1); mbar_init(&empty_bar[s], 1); }
@@ -950,16 +976,17 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
     // Lane i owns elements 2i, 2i+1 of the row's 64-element k-block slice, so a warp-level load walks the (dx, c)-contiguous
     // runs of the NHWC image (coalesced), and its 32 x 4-byte shared-memory stores fill exactly one swizzled 128-byte row.
     const int gw = warp;                              // 0..7: rows gw*16 .. gw*16+15 of the tile
+    const float sc = p.inv_ls * kXScale;              // patches are staged as xs * kXScale
     int stage = 0; uint32_t phase = 0; uint32_t tile = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
       const int tt = item / p.njt, jt = item - tt * p.njt;
       // per-row image base (lanes 0..15 compute the warp's 16 rows, broadcast by shuffle below); -1 marks rows beyond T
-      long long my_base = -1;
+      int my_base = -1;
       if (lane < 16) {
         const int t = tt * kBM + gw * 16 + lane;
         if (t < p.T) {
           const int n = t / p.v.P, pp = t - n * p.v.P;
-          my_base = (long long)n * p.v.HWC + p.v.patch_base(pp);
+          my_base = n * p.v.HWC + p.v.patch_base(pp);     // < 2^31 (checked by the host)
         }
       }
       float xxp[16];
@@ -972,9 +999,9 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
         float x0[16], x1[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {                // all 32 loads of the k-block in flight before the slot wait
-          const long long base = __shfl_sync(0xffffffffu, my_base, i);
+          const int base = __shfl_sync(0xffffffffu, my_base, i);
           const float* src = p.X + (base < 0 ? 0 : base);
-          const float msk = base < 0 ? 0.f : p.inv_ls;
+          const float msk = base < 0 ? 0.f : sc;
           x0[i] = in0 ? __ldg(src + o0) * msk : 0.f;
           x1[i] = in1 ? __ldg(src + o1) * msk : 0.f;
         }
@@ -985,16 +1012,15 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
           tma_load_2d(st + 2 * Cfg::kStageA, &tmZ_hi, &full_bar[stage], kb * kBK, jt * BN);
           tma_load_2d(st + 2 * Cfg::kStageA + Cfg::kStageB, &tmZ_lo, &full_bar[stage], kb * kBK, jt * BN);
         }
+        // element pair `lane` of row r: 16-byte chunk lane/4 (XOR-swizzled with r mod 8), 4-byte slot lane%4 inside it
+        uint8_t* row0 = st + gw * 2048 + ((lane & 3) << 2);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int r = gw * 16 + i;
           xxp[i] = fmaf(x0[i], x0[i], fmaf(x1[i], x1[i], xxp[i]));
-          const float s0 = x0[i] * kXScale, s1 = x1[i] * kXScale;
-          const __half2 hi = __floats2half2_rn(s0, s1);
+          const __half2 hi = __floats2half2_rn(x0[i], x1[i]);
           const float2 hf = __half22float2(hi);
-          const __half2 lo = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
-          // element pair `lane` of row r: 16-byte chunk lane/4 (XOR-swizzled with r mod 8), 4-byte slot lane%4 inside it
-          uint8_t* dst = st + (r >> 3) * 1024 + (r & 7) * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2);
+          const __half2 lo = __floats2half2_rn(x0[i] - hf.x, x1[i] - hf.y);
+          uint8_t* dst = row0 + (i >> 3) * 1024 + (i & 7) * 128 + (((lane >> 2) ^ (i & 7)) << 4);
           *reinterpret_cast<__half2*>(dst) = hi;
           *reinterpret_cast<__half2*>(dst + Cfg::kStageA) = lo;
         }
@@ -1004,7 +1030,9 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
             float v = xxp[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) xx_s[(tile & 3) * kBM + gw * 16 + i] = v;
+            // exponent offset of the row: -0.5 log2(e) |xs_t|^2 (xxp is in kXScale^2 units); rows beyond T give exp2(-inf) = 0
+            const int base = __shfl_sync(0xffffffffu, my_base, i);
+            if (lane == 0) xx_s[(tile & 3) * kBM + gw * 16 + i] = base < 0 ? -INFINITY : -0.5f * c2 * v;
           }
         }
         fence_proxy_async();                        // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -1047,13 +1075,12 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: exp + split; 2 warps per lane quarter
+    // ------------------------------------------------------------------ epilogue: exp2 + split; 2 warps per lane quarter
     const int ew = warp - kKufGatherWarps - 1;      // 0..7
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int chalf = ew >> 2;                       // which half of the BN columns
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const float ks = p.kscal[0] * p.variance;
-    const float dscale = 2.f / (kXScale * kXScale);
+    constexpr int CW = BN / 2, NCH = CW / 32;        // columns per thread, 32-column chunks
     uint32_t tile = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++tile) {
       const int tt = item / p.njt, jt = item - tt * p.njt;
@@ -1062,32 +1089,33 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
       const uint32_t buf = tile & 1, use = tile >> 1;
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
-      const float xx = xx_s[(tile & 3) * kBM + row];
-      const bool valid = t < p.T;
-      const uint32_t taddr = tmem_base + lane_base + buf * BN;
-      __half* oh = p.Kh + t * p.Mp + jt * BN;
-      __half* ol = p.Kl + t * p.Mp + jt * BN;
-#pragma unroll 1
-      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-        float v[32];
-        tmem_ld_32x32(taddr + c, v);
+      const float xc = xx_s[(tile & 3) * kBM + row];
+      const uint32_t taddr = tmem_base + lane_base + buf * BN + chalf * CW;
+      const int m0 = jt * BN + chalf * CW;
+      __half* oh = p.Kh + t * p.Mp + m0;
+      __half* ol = p.Kl + t * p.Mp + m0;
+      uint32_t v[2][32];                             // two chunks in flight: the next TMEM read overlaps this chunk's math
+      tmem_ld_32x32_nowait(taddr, v[0]);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        tmem_ld_wait();
+        if (ch + 1 < NCH) tmem_ld_32x32_nowait(taddr + (ch + 1) * 32, v[(ch + 1) & 1]);
+        const uint32_t* vc = v[ch & 1];
         __align__(16) __half2 hi[16];
         __align__(16) __half2 lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int m = jt * BN + c + 2 * i;
-          const float2 zz2 = __ldg(reinterpret_cast<const float2*>(p.zz + m));
-          const float d0 = xx + zz2.x - dscale * v[2 * i], d1 = xx + zz2.y - dscale * v[2 * i + 1];
-          const float k0 = (valid && m < p.M) ? ks * __expf(-0.5f * d0) : 0.f;
-          const float k1 = (valid && m + 1 < p.M) ? ks * __expf(-0.5f * d1) : 0.f;
+          const float2 zc2 = *reinterpret_cast<const float2*>(zc_s + m0 + ch * 32 + 2 * i);
+          const float k0 = exp2f(fmaf(c2, __uint_as_float(vc[2 * i]), zc2.x + xc));
+          const float k1 = exp2f(fmaf(c2, __uint_as_float(vc[2 * i + 1]), zc2.y + xc));
           hi[i] = __floats2half2_rn(k0, k1);
           const float2 hf = __half22float2(hi[i]);
           lo[i] = __floats2half2_rn(k0 - hf.x, k1 - hf.y);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          reinterpret_cast<uint4*>(oh + c)[i] = reinterpret_cast<uint4*>(hi)[i];
-          reinterpret_cast<uint4*>(ol + c)[i] = reinterpret_cast<uint4*>(lo)[i];
+          reinterpret_cast<uint4*>(oh + ch * 32)[i] = reinterpret_cast<uint4*>(hi)[i];
+          reinterpret_cast<uint4*>(ol + ch * 32)[i] = reinterpret_cast<uint4*>(lo)[i];
         }
       }
       tc_fence_before();
@@ -1148,7 +1176,7 @@ static int launch_kuf_tc(const TcPrep& prep, const View& v, const float* X, int 
   p.n_items = ceil_div(p.T, kBM) * p.njt;
   p.nkb = ceil_div(v.L, kBK);
   p.inv_ls = inv_ls; p.variance = variance; p.zz = prep.zz; p.kscal = kscal; p.Kh = (__half*)Kh; p.Kl = (__half*)Kl;
-  const int smem_bytes = Cfg::kSmemBytes + 8 * kBM * 4 + ceil_div(v.L, kBK) * kBK * 4 + 64;
+  const int smem_bytes = Cfg::kSmemBytes + 8 * kBM * 4 + ceil_div(v.L, kBK) * kBK * 4 + prep.Mp * 4 + 64;
   if (smem_bytes > 227 * 1024) { set_error("kuf_tc: patch length %d too large", v.L); return DCGP_ERR_ARG; }
   static int attr_bytes = 0;
   const bool attr = attr_bytes >= smem_bytes;
