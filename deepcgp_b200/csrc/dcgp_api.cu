@@ -322,9 +322,9 @@ size_t dcgp_prepare_workspace_bytes(const dcgp_layer_desc* d) {
   return carve_f64(d->M, d->R, nullptr).bytes;
 }
 
-int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
-                       const double* q_sqrt, int algo, void* prep_buf, double* kl, void* ws, size_t ws_bytes, int* info,
-                       void* stream) {
+int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
+                          const double* q_sqrt, int algo, void* prep_buf, double* kl, void* ws, size_t ws_bytes, int* info,
+                          void* fwd_ready_event, void* stream) {
   DCGP_TRY(check_desc(d));
   if (!Z || !q_mu || !q_sqrt || !prep_buf || !kl || !info) { set_error("layer_prepare: null argument"); return DCGP_ERR_ARG; }
   F64Work w = carve_f64(d->M, d->R, ws);
@@ -354,7 +354,6 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
     Lpinv = w.Lpinv;
   }
   DCGP_TRY(factor_and_G(w, d->white, q_mu, info, &gi, st));
-  if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
   if (algo == DCGP_ALGO_TC) {
     if (d->white) {   // Q_0 = Kuu^-1 is needed by the backward operands even when G = Lm^-1
       GemmF64 g{};
@@ -364,11 +363,18 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
       g.C = w.Kinv; g.ldc = M; g.alpha = 1.0; g.batch = 1;
       DCGP_TRY(gemm_f64(g, st));
     }
+    // forward operands first; the caller's event marks the point from which dcgp_layer_apply may run -- the KL (which
+    // joins the prior chain) and the backward operands follow on the same stream, off the forward's critical path
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, st));
+                               w.beta, w.sc + 1, w.Kinv, 1, st));
     DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+    if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
+    if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
+    DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
+                               w.beta, w.sc + 1, w.Kinv, 2, st));
     return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
   }
+  if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
   if (own_prior) {   // the fp64 path needs w.Wr for W_r first: move the prior factor out of the way
     cudaMemcpyAsync(w.Kinv == gi.G ? w.tmpK : w.Kinv, Kp, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToDevice, st);
     Lp = (w.Kinv == gi.G) ? w.tmpK : w.Kinv;
@@ -376,7 +382,14 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
   DCGP_TRY(wr_f64(w, d->white, gi, q_sqrt, st));
   DCGP_TRY(launch_pack_w(w.Linv, w.Mq, w.Wr, M, p.Mp, R, p.W, st));
   DCGP_TRY(launch_pack_wmean(w.beta, M, p.Mp, R, p.RP, p.Wmean, st));
+  if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
   return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st);
+}
+
+int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
+                       const double* q_sqrt, int algo, void* prep_buf, double* kl, void* ws, size_t ws_bytes, int* info,
+                       void* stream) {
+  return dcgp_layer_prepare_ev(d, Z, Z_prior, q_mu, q_sqrt, algo, prep_buf, kl, ws, ws_bytes, info, nullptr, stream);
 }
 
 int dcgp_prepare_workspace_layout(const dcgp_layer_desc* d, size_t* off_kinv, size_t* off_linv, size_t* off_lpinv, int* ld_inv) {

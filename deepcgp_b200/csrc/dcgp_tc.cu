@@ -822,29 +822,44 @@ int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double*
 // Linv/G/Lpinv/beta are float64 (Cholesky-quality); only these products run split-fp16 on tcgen05.
 int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
                       const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out,
-                      const double* Kinv, cudaStream_t st) {
+                      const double* Kinv, int parts, cudaStream_t st) {
   const int M = t.M, Mp = t.Mp, R = t.R;
   int rc;
-  cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
-  if ((rc = maxabs_f64(q_sqrt, (long long)R * M, M, M, M, t.mx + 2, st))) return rc;
-  if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc;
-  if (Lpinv && (rc = maxabs_f64(Lpinv, M, M, ldp, 0, t.mx + 4, st))) return rc;
-  scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 2, 3, t.scal);
-  check_launch("scales_from_max");
-  // QT[r*Mp + i, k] = L_r[k, i]  (transpose of the lower-triangular q_sqrt_r)
-  if ((rc = pack_planes_f64(q_sqrt, M, (long long)M * M, M, M, 1, 1, R, Mp, Mp, t.scal + 4, t.QTh, t.QTl, st))) return rc;
-  // B operand of W_r: B[j, k] = G[k, j]  (G symmetric when it is Kuu^-1; the transpose of Lm^-1 when whitened)
-  if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
-  TcGemm g;
-  memset(&g, 0, sizeof(g));
-  g.Ah = t.QTh; g.Al = t.QTl; g.a_rows_total = (long long)R * Mp; g.a_batch_rows = Mp;
-  g.Bh = t.Gh; g.Bl = t.Gl; g.b_rows_total = Mp; g.b_batch_rows = 0;
-  g.batch = R; g.m = M; g.n = M; g.m_pad = Mp; g.n_pad = Mp; g.k_pad = Mp;
-  g.a_scal = t.scal + 4; g.b_scal = t.scal + 6;
-  g.C = t.Wr32; g.c_batch_stride = (long long)Mp * Mp; g.ldc = Mp;
-  if (M != Mp) cudaMemsetAsync(t.Wr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);   // padding must not poison the max scan
-  if ((rc = tc_gemm(g, st))) return rc;
+  if (parts & 1) {
+    // ---- part 1: what the forward conditional GEMM needs (W planes)
+    cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
+    if ((rc = maxabs_f64(q_sqrt, (long long)R * M, M, M, M, t.mx + 2, st))) return rc;
+    if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc;
+    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 2, 2, t.scal);
+    check_launch("scales_from_max");
+    // QT[r*Mp + i, k] = L_r[k, i]  (transpose of the lower-triangular q_sqrt_r)
+    if ((rc = pack_planes_f64(q_sqrt, M, (long long)M * M, M, M, 1, 1, R, Mp, Mp, t.scal + 4, t.QTh, t.QTl, st))) return rc;
+    // B operand of W_r: B[j, k] = G[k, j]  (G symmetric when it is Kuu^-1; the transpose of Lm^-1 when whitened)
+    if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
+    TcGemm g;
+    memset(&g, 0, sizeof(g));
+    g.Ah = t.QTh; g.Al = t.QTl; g.a_rows_total = (long long)R * Mp; g.a_batch_rows = Mp;
+    g.Bh = t.Gh; g.Bl = t.Gl; g.b_rows_total = Mp; g.b_batch_rows = 0;
+    g.batch = R; g.m = M; g.n = M; g.m_pad = Mp; g.n_pad = Mp; g.k_pad = Mp;
+    g.a_scal = t.scal + 4; g.b_scal = t.scal + 6;
+    g.C = t.Wr32; g.c_batch_stride = (long long)Mp * Mp; g.ldc = Mp;
+    if (M != Mp) cudaMemsetAsync(t.Wr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);   // padding must not poison the max scan
+    if ((rc = tc_gemm(g, st))) return rc;
+    // W planes for the conditional GEMM: block 0 = Lm^-1 (float64), blocks 1..R = W_r (fp32 product), mean rows = beta^T
+    if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 0, st))) return rc;
+    if ((rc = maxabs_f32(t.Wr32, (long long)R * Mp * Mp, t.mx + 0, st))) return rc;
+    if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 1, st))) return rc;
+    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
+    pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
+                                                     (__half*)t.Wh, (__half*)t.Wl);
+    if ((rc = check_launch("tc_build_operands", 2))) return rc;
+  }
+  if (!(parts & 2)) return DCGP_OK;
+  // ---- part 2: KL trace and the backward operands (not needed by the forward conditional)
   if (Lpinv) {
+    if ((rc = maxabs_f64(Lpinv, M, M, ldp, 0, t.mx + 4, st))) return rc;
+    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 4, 1, t.scal);
+    check_launch("scales_from_max");
     if ((rc = pack_planes_f64(Lpinv, ldp, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 8, t.Lph, t.Lpl, st))) return rc;
     cudaMemsetAsync(trace_out, 0, sizeof(double), st);
     TcGemm h;
@@ -856,14 +871,6 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
     h.sq_out = trace_out;
     if ((rc = tc_gemm(h, st))) return rc;
   }
-  // W planes for the conditional GEMM: block 0 = Lm^-1 (float64), blocks 1..R = W_r (fp32 product), mean rows = beta^T
-  if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 0, st))) return rc;
-  if ((rc = maxabs_f32(t.Wr32, (long long)R * Mp * Mp, t.mx + 0, st))) return rc;
-  if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 1, st))) return rc;
-  scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
-  pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
-                                                   (__half*)t.Wh, (__half*)t.Wl);
-  if ((rc = check_launch("tc_build_operands", 2))) return rc;
   if (!Kinv) return DCGP_OK;
   // ---- backward operands: B_r = G L_r (= W_r^T), Q_r = B_r B_r^T, QB planes [Mp, Jp] = [2Q_0 | ... | 2Q_R | beta | 0]
   {

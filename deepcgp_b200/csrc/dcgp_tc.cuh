@@ -34,7 +34,7 @@ int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double*
                      int R, cudaStream_t st);
 int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
                       const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out,
-                      const double* Kinv, cudaStream_t st);
+                      const double* Kinv, int parts, cudaStream_t st);   // parts: 1 = forward operands, 2 = KL trace + backward operands
 int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st);
 
 struct TcCondWork {

@@ -150,6 +150,8 @@ class _PatchGPLayer(Layer):
         self._info = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._hold = False
         self._ready = None      # CUDA event recorded after prepare() when it ran on a side stream
+        self._ready_fwd = None  # ... and the earlier point from which the forward operands are complete (set by prepare())
+        self._ev_fwd = None
         self._pending = None    # set by grad.TrainStep: finishes this layer's pipelined update + prepare() (lazy, see there)
         self.algo = None
         if q_sqrt is None:
@@ -189,10 +191,14 @@ class _PatchGPLayer(Layer):
         Z = _lib.f64(self.feature.Z, dev)
         Zp = self._Z_prior()
         self._keep = (Z, Zp, _lib.f64(self.q_mu, dev), torch.tril(_lib.f64(self.q_sqrt, dev)).contiguous())
-        _lib.check(_lib.lib.dcgp_layer_prepare(d, _lib.ptr(Z), _lib.ptr(Zp), _lib.ptr(self._keep[2]),
-                                               _lib.ptr(self._keep[3]), self._algo(), _lib.ptr(self._prep),
-                                               _lib.ptr(self._kl), _lib.ptr(ws), ws.numel(), _lib.ptr(self._info),
-                                               _lib.stream()))
+        if self._ev_fwd is None:
+            self._ev_fwd = torch.cuda.Event()
+            self._ev_fwd.record()               # forces the underlying cudaEvent_t into existence
+        _lib.check(_lib.lib.dcgp_layer_prepare_ev(d, _lib.ptr(Z), _lib.ptr(Zp), _lib.ptr(self._keep[2]),
+                                                  _lib.ptr(self._keep[3]), self._algo(), _lib.ptr(self._prep),
+                                                  _lib.ptr(self._kl), _lib.ptr(ws), ws.numel(), _lib.ptr(self._info),
+                                                  self._ev_fwd.cuda_event, _lib.stream()))
+        self._ready_fwd = self._ev_fwd          # recorded inside the call, once the forward operands were queued
         if check:
             _lib.raise_if_not_pd(self._info)
 
@@ -205,8 +211,8 @@ class _PatchGPLayer(Layer):
         self._run_pending()
         if not self._hold:
             self.prepare()
-        elif self._ready is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._ready)
+        elif self._ready is not None:           # prepare() ran on a side stream: wait for its forward operands only
+            torch.cuda.current_stream(self.device).wait_event(self._ready_fwd or self._ready)
         d = self._desc()
         X = _lib.f32(X, self.device)
         n_rows = X.shape[0]

@@ -121,6 +121,12 @@ int dcgp_prepare_layout(const dcgp_layer_desc* d, size_t* off_b32, int* ld_b);
 int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
                        const double* q_sqrt, int algo, void* prep, double* kl, void* ws, size_t ws_bytes,
                        int* info, void* stream);
+/* Same, and records the CUDA event `fwd_ready_event` (a cudaEvent_t, may be NULL) on `stream` as soon as the operands
+ * dcgp_layer_apply needs are complete; the KL and the backward-pass operands follow on the same stream.  Lets a host
+ * that runs the prepare on a side stream start the layer's forward before the whole call has drained. */
+int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
+                          const double* q_sqrt, int algo, void* prep, double* kl, void* ws, size_t ws_bytes, int* info,
+                          void* fwd_ready_event, void* stream);
 
 /* The minibatch-sized work of one layer: layers.py:96-135 ConvLayer.conditional_ND or
  * DS/layers.py:191-229 SVGP_Layer.conditional_ND (with kernels.py:106-133 Kzx/Kdiag), followed by the
