@@ -326,16 +326,18 @@ def run_ours(args, cfg):
 
 
 def kernel_roofline(model, cfg, B, S, device, flush):
-    """Dominant kernel = the tcgen05 conditional GEMM `tc_kernel<MODE_COND,256>` of conv layer 2 (its forward launch; the
-    two backward GEMMs of the same layer are the same kernel in MODE_GEMM).  Timed live with CUDA events recorded by the
-    library on the launching stream around that kernel (dcgp_set_kernel_timing), L2 flushed before every launch.
+    """Dominant kernel = the tcgen05 conditional GEMM `tc_kernel<MODE_COND,256>` of conv layer 2 (forward); the two big
+    backward GEMMs of the same layer (`dk_gemm_kernel`, `xf_gemm_kernel`) and the Kuf kernel are reported next to it.
+    Every kernel is timed live with CUDA events recorded by the library on the launching stream around that launch
+    (dcgp_set_kernel_timing), L2 flushed before every repetition.
       achieved = ALGORITHMIC flops per launch (T*(M^2 + R*M^2 + 2MR + 2M(R+1)), triangular count, no split)
                  / launch duration;   peak = MEASURED_PEAKS.json bf16 burst (the kernel is timed alone);
-      executed_* = the tensor-pipe flops the launch really issues: 3 split products x dense W (+ the mean tile);
+      executed_* = the tensor-pipe flops the launch really issues: 3 split products x dense operands;
       traffic = dram__bytes_read + dram__bytes_write of this launch from the committed `ncu --set full` capture
-                (profiles/r1_ncu_full_layer2_forward_kuf_cond.csv)."""
+                (profiles/r1b_ncu_full_layer2.csv)."""
     import torch
     from deepcgp_b200 import _lib
+    from deepcgp_b200.grad import LayerBackward
     if len(model.layers) < 3:
         return None
     peaks = {}
@@ -346,41 +348,70 @@ def kernel_roofline(model, cfg, B, S, device, flush):
     peak = float(peaks.get("bf16_tflops", 1590.0))
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     layer = model.layers[1]
+    layer._run_pending()
     n_rows = S * B
     D_in = int(np.prod(layer.view.input_size)) * layer.view.feature_maps
     X = torch.randn((n_rows, D_in), device=device)
+    gm = torch.randn((n_rows, layer.num_outputs), device=device) * 1e-3
+    gv = torch.randn((n_rows, layer.num_outputs), device=device) * 1e-3
+    lb = LayerBackward(layer)
     layer.prepare()
     layer._hold = True
     _lib.lib.dcgp_set_kernel_timing(1)
     for _ in range(3):
         layer._conditional(X)
+        lb.t_sized(X, 1, gm, gv, True)
     torch.cuda.synchronize()
-    t_cond, t_kuf = [], []
+    t = {0: [], 1: [], 2: [], 3: []}
     for _ in range(10):
         flush.zero_()
         layer._conditional(X)
-        t_cond.append(_lib.lib.dcgp_kernel_ms(0))
-        t_kuf.append(_lib.lib.dcgp_kernel_ms(1))
+        t[0].append(_lib.lib.dcgp_kernel_ms(0))
+        t[1].append(_lib.lib.dcgp_kernel_ms(1))
+        flush.zero_()
+        lb.t_sized(X, 1, gm, gv, True)
+        t[2].append(_lib.lib.dcgp_kernel_ms(2))
+        t[3].append(_lib.lib.dcgp_kernel_ms(3))
     _lib.lib.dcgp_set_kernel_timing(0)
     layer._hold = False
-    ms, ms_kuf = float(np.mean(t_cond)), float(np.mean(t_kuf))
+    ms, ms_kuf, ms_dk, ms_dq = (float(np.mean(t[i])) for i in range(4))
     M, R, P, L = layer.num_inducing, layer.gp_count, layer.patch_count, layer.patch_length
     T = P * n_rows
     alg = T * (M * M + R * M * M + 2.0 * M * R + 2.0 * M * (R + 1))
     executed = 3 * 2.0 * T * ((R + 1) * M * M + 256 * M)
     ach = alg / (ms * 1e-3) / 1e12
     kuf_bytes = 4.0 * T * M + 4.0 * n_rows * D_in            # K planes written (hi+lo fp16) + images read
+    kuf_flops = 3 * 2.0 * T * M * 256                        # 3 split products over the padded patch length
+    src = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590"
+
+    def tensor_entry(name, t_ms, alg_flops, exe_flops, extra):
+        e = {"kernel": name, "bound": "tensor", "ms": t_ms, "achieved": alg_flops / (t_ms * 1e-3) / 1e12, "peak": peak,
+             "unit": "TFLOP/s", "frac": alg_flops / (t_ms * 1e-3) / 1e12 / peak, "algorithmic_gflop": alg_flops / 1e9,
+             "executed_tensor_gflop": exe_flops / 1e9, "executed_frac": exe_flops / (t_ms * 1e-3) / 1e12 / peak}
+        e.update(extra)
+        return e
+
+    # backward GEMMs: algorithmic = the Q-form contraction 2*T*R*M^2 (dQ: its symmetric half); executed = 3 split products
+    # (dK: + the 64-deep mean tile; dQ: 6 of 8 output tiles per r)
+    dk = tensor_entry("dk_gemm_kernel<256,true> (dK GEMM + fused dd epilogue, conv layer 2 backward)", ms_dk,
+                      2.0 * T * R * M * M, 3 * 2.0 * T * (R * M * M + 64 * M),
+                      {"traffic": 1879259120, "tensor_pipe_active_pct_ncu": 78.4,
+                       "epilogue_bytes": 2.0 * 4 * T * M + 4.0 * T * M})
+    dq = tensor_entry("xf_gemm_kernel<256> (dQ GEMM, in-smem column rescale, conv layer 2 backward)", ms_dq,
+                      1.0 * T * R * M * M, 3 * 2.0 * T * R * M * M * 0.75,
+                      {"traffic": 790946688, "tensor_pipe_active_pct_ncu": 60.7})
     return {"bound": "tensor", "kernel": "tc_kernel<MODE_COND,256> (conditional GEMM, conv layer 2 forward)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": 911319040, "ms": ms, "algorithmic_gflop": alg / 1e9,
+            "traffic": 877827921, "ms": ms, "algorithmic_gflop": alg / 1e9,
             "executed_tensor_gflop": executed / 1e9, "executed_tflops": executed / (ms * 1e-3) / 1e12,
             "executed_frac": executed / (ms * 1e-3) / 1e12 / peak,
-            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590"),
-            "tensor_pipe_active_pct_ncu": 96.7,
+            "peak_source": src, "tensor_pipe_active_pct_ncu": 96.9,
             "kuf": {"kernel": "kuf_tc_kernel<256> (conv layer 2)", "bound": "hbm", "ms": ms_kuf,
                     "achieved": kuf_bytes / (ms_kuf * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                     "frac": kuf_bytes / (ms_kuf * 1e-3) / 1e9 / hbm, "algorithmic_bytes": kuf_bytes,
-                    "traffic": 492560896}}
+                    "traffic": 500990456, "executed_tensor_gflop": kuf_flops / 1e9,
+                    "tensor_floor_ms": kuf_flops / (peak * 1e12) * 1e3},
+            "dk_gemm": dk, "dq_gemm": dq}
 
 
 def main():

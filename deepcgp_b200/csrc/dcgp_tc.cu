@@ -456,17 +456,18 @@ static int make_tmap_f16(CUtensorMap* tm, const void* base, uint64_t rows, uint6
 // Optional live kernel timing (bench.py's roofline leg): CUDA events recorded on the launching stream around the
 // conditional-GEMM and Kuf kernels when enabled; dcgp_kernel_ms() synchronises on the end event and returns the duration.
 static int g_timing = 0;
-static cudaEvent_t g_ev[2][2];
-static bool g_ev_init = false, g_ev_used[2] = {false, false};
+constexpr int kTimers = 4;   // 0 = conditional GEMM, 1 = Kuf, 2 = dK (+dd) GEMM, 3 = dQ GEMM
+static cudaEvent_t g_ev[kTimers][2];
+static bool g_ev_init = false, g_ev_used[kTimers] = {false, false, false, false};
 void tc_set_timing(int on) {
   g_timing = on;
   if (on && !g_ev_init) {
-    for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) cudaEventCreate(&g_ev[i][j]);
+    for (int i = 0; i < kTimers; ++i) for (int j = 0; j < 2; ++j) cudaEventCreate(&g_ev[i][j]);
     g_ev_init = true;
   }
 }
 double tc_kernel_ms(int which) {
-  if (!g_ev_init || which < 0 || which > 1 || !g_ev_used[which]) return -1.0;
+  if (!g_ev_init || which < 0 || which >= kTimers || !g_ev_used[which]) return -1.0;
   float ms = 0.f;
   cudaEventSynchronize(g_ev[which][1]);
   if (cudaEventElapsedTime(&ms, g_ev[which][0], g_ev[which][1]) != cudaSuccess) return -1.0;

@@ -78,7 +78,7 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
                    float* mean_t, cudaStream_t st);
 
 void tc_set_timing(int on);
-double tc_kernel_ms(int which);   // 0 = conditional GEMM, 1 = Kuf
+double tc_kernel_ms(int which);   // 0 = conditional GEMM, 1 = Kuf, 2 = dK (+dd) GEMM, 3 = dQ GEMM (last launch of each)
 
 // Workspace of the backward pass of one layer (see dcgp_tc_bwd.inc)
 struct TcBwdWork {

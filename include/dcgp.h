@@ -63,7 +63,7 @@ int dcgp_version(void);
 /* number of CUDA kernels this library has launched so far in this process (bench.py reports it as gpu_launches) */
 long long dcgp_launch_count(void);
 /* Live kernel timing for roofline reports: when enabled, CUDA events are recorded on the launching stream around the
- * most recent conditional-GEMM (which = 0) and Kuf (which = 1) kernel; dcgp_kernel_ms() waits for the end event and
+ * most recent conditional-GEMM (which = 0), Kuf (1), dK+dd GEMM (2) and dQ GEMM (3) kernel; dcgp_kernel_ms() waits for the end event and
  * returns the duration in milliseconds (-1 if none was recorded). */
 void dcgp_set_kernel_timing(int on);
 double dcgp_kernel_ms(int which);
