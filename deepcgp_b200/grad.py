@@ -33,6 +33,8 @@ def softplus_inv(x):
 class LayerBackward(object):
     """Per-layer buffers + the M-only chain rule."""
 
+    BATCHED_DTYPE = torch.float32     # dtype of the R-batched M^3 products of the chain rule (torch.float64 = all-double)
+
     def __init__(self, layer):
         self.layer = layer
         d = layer._desc()
@@ -147,26 +149,37 @@ class LayerBackward(object):
         Kn, D = self._rbf_parts(Z, var, ls)
         # Kuu^-1 and the prior's Lp^-1 were already formed (float64) by this step's dcgp_layer_prepare: re-use them
         Kinv, Lpinv = self._forward_inverses()
+        conv = isinstance(layer, ConvLayer)
+        bt = self.BATCHED_DTYPE
+
+        def stack(T3):                                                   # [R,M,M] -> [M, R*M]: sum_r A_r B_r^T as ONE GEMM
+            return T3.permute(1, 0, 2).reshape(M, R * M)
+
+        # The R-batched M^3 products run in BATCHED_DTYPE (float32 by default: their inputs -- dQ from the split-fp16
+        # GEMMs, B_r from the forward -- carry 22-24 bits anyway, and cuBLAS float64 batched GEMMs reach only ~5 TFLOP/s
+        # here: 80 % of this chain at M=512, 90 % at M=1024); everything single-matrix stays float64.
+        Lqb = Lq.to(bt)
+        Kinvb = Kinv.to(bt)
         if layer._algo() == _lib.ALGO_TC:
-            B = self._forward_B().to(torch.float64)                      # [R,M,M] = Kinv @ Lq, already formed this step
+            Bb = self._forward_B().to(bt)                                # [R,M,M] = Kinv @ Lq, already formed this step
         else:
-            B = Kinv @ Lq
-        U = (gQ[1:] + gQ[1:].transpose(1, 2)) @ B                        # d/dB_r
-        gLq = Kinv @ U                                                   # d/dL_r (through B_r)
-        GK = gQ[0] + torch.einsum("rij,rkj->ik", U, Lq) + gbeta @ q_mu.T # d/dKinv
+            Bb = Kinvb @ Lqb
+        Ub = (gQ[1:] + gQ[1:].transpose(1, 2)).to(bt) @ Bb               # d/dB_r
+        gLq = (Kinvb @ Ub).to(torch.float64)                             # d/dL_r (through B_r)
+        GK = gQ[0] + (stack(Ub) @ stack(Lqb).T).to(torch.float64) + gbeta @ q_mu.T   # d/dKinv
         g_qmu = Kinv @ gbeta
         GU = -(Kinv @ GK @ Kinv)                                         # d/dKuu
-        conv = isinstance(layer, ConvLayer)
         if conv:    # prior = Kuu at the initial Z (a constant) with the live hyper-parameters (layers.py:149-150)
             Zp = layer.Z_prior.to(torch.float64)
             Kpn, Dp = self._rbf_parts(Zp, var, ls)
             Kpinv = Lpinv.T @ Lpinv
-            C = Kpinv @ Lq
+            Cb = Kpinv.to(bt) @ Lqb
             a = Kpinv @ q_mu
         else:
-            Kpinv, C, a = Kinv, B, g_qmu.new_empty(0)
+            Kpinv, Cb = Kinv, Bb
             a = Kinv @ q_mu
-        dKL_dKp = 0.5 * (-(a @ a.T) - torch.einsum("rij,rkj->ik", C, C) + R * Kpinv)
+        C = Cb.to(torch.float64)
+        dKL_dKp = 0.5 * (-(a @ a.T) - (stack(Cb) @ stack(Cb).T).to(torch.float64) + R * Kpinv)
         g_qmu = g_qmu - kl_weight * a
         gLq = gLq - kl_weight * (C - torch.diag_embed(1.0 / torch.diagonal(Lq, dim1=1, dim2=2)))
         if conv:
