@@ -7,6 +7,7 @@ NOTE (round 1): that M-only chain rule is evaluated with torch.autograd over tor
 it is O(R M^3), independent of the batch, and is the one place on the step where library kernels are used.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -77,14 +78,14 @@ class LayerBackward(object):
             _lib.ptr(self.gw) if layer._kind == _lib.LAYER_SVGP_CONV else None, _lib.ptr(ws), ws.numel(), phases,
             _lib.stream()))
 
-    def m_only(self, kl_weight=1.0, hyp=None):
+    def m_only(self, kl_weight=1.0, hyp=None, static=None):
         """Chain rule through the minibatch-independent operands; returns d ELBO / d{Z, variance, lengthscale, q_mu,
         q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that summing over ranks counts the KL once.
         `hyp` (optional): device tensor [variance, lengthscale] to use instead of the host floats -- keeps the whole chain
         free of host values so that it can be captured in a CUDA graph (TrainStep)."""
         if self.layer.white:
             return self._m_only_autograd(kl_weight)
-        return self._m_only_closed_form(kl_weight, hyp)
+        return self._m_only_closed_form(kl_weight, hyp, static)
 
     @staticmethod
     def _rbf_parts(Z, var, ls):
@@ -131,15 +132,13 @@ class LayerBackward(object):
         return layer._prep[ob:ob + R * ld * ld * 4].view(torch.float32).view(R, ld, ld)[:, :M, :M]
 
     @torch.no_grad()
-    def _m_only_closed_form(self, kl_weight, hyp=None):
-        """Non-whitened case, written out as ~15 batched float64 GEMMs (no autograd graph, no triangular solves):
-             Q_0 = Kinv, Q_r = B_r B_r^T with B_r = Kinv L_r, beta = Kinv q_mu       (Kinv = Kuu^-1)
-             KL  = 1/2 [q_mu^T Kp^-1 q_mu - MR - sum log diag(L_r)^2 + sum <L_r, Kp^-1 L_r> + R log|Kp|]"""
+    def m_only_static(self, kl_weight=1.0, hyp=None):
+        """The part of the (non-whitened) chain rule that depends only on the parameters and on this step's
+        dcgp_layer_prepare -- Kuu and its distance matrix, the KL gradient, the operand casts -- i.e. everything that can be
+        computed BEFORE the layer's dQ / dbeta exist.  TrainStep runs it on the layer's side stream during the forward
+        pass, which takes ~40 % of the chain off the serial tail of the step."""
         layer = self.layer
-        dev = layer.device
-        M, R, Mp = self.M, self.R, self.Mp
-        gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
-        gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
+        M, R = self.M, self.R
         Z = layer.feature.Z.to(torch.float64)
         if hyp is None:
             var, ls = float(layer._base_kernel.variance), float(layer._base_kernel.lengthscales)
@@ -164,11 +163,6 @@ class LayerBackward(object):
             Bb = self._forward_B().to(bt)                                # [R,M,M] = Kinv @ Lq, already formed this step
         else:
             Bb = Kinvb @ Lqb
-        Ub = (gQ[1:] + gQ[1:].transpose(1, 2)).to(bt) @ Bb               # d/dB_r
-        gLq = (Kinvb @ Ub).to(torch.float64)                             # d/dL_r (through B_r)
-        GK = gQ[0] + (stack(Ub) @ stack(Lqb).T).to(torch.float64) + gbeta @ q_mu.T   # d/dKinv
-        g_qmu = Kinv @ gbeta
-        GU = -(Kinv @ GK @ Kinv)                                         # d/dKuu
         if conv:    # prior = Kuu at the initial Z (a constant) with the live hyper-parameters (layers.py:149-150)
             Zp = layer.Z_prior.to(torch.float64)
             Kpn, Dp = self._rbf_parts(Zp, var, ls)
@@ -178,18 +172,41 @@ class LayerBackward(object):
         else:
             Kpinv, Cb = Kinv, Bb
             a = Kinv @ q_mu
-        C = Cb.to(torch.float64)
         dKL_dKp = 0.5 * (-(a @ a.T) - (stack(Cb) @ stack(Cb).T).to(torch.float64) + R * Kpinv)
-        g_qmu = g_qmu - kl_weight * a
-        gLq = gLq - kl_weight * (C - torch.diag_embed(1.0 / torch.diagonal(Lq, dim1=1, dim2=2)))
+        g_qmu_kl = -kl_weight * a
+        gLq_kl = -kl_weight * (Cb.to(torch.float64) - torch.diag_embed(1.0 / torch.diagonal(Lq, dim1=1, dim2=2)))
         if conv:
             gvar_p, gls_p, _ = self._rbf_chain(-kl_weight * dKL_dKp, Kpn, Dp, Zp, var, ls, need_Z=False)
+            GU_kl = None
         else:
-            GU = GU - kl_weight * dKL_dKp
+            GU_kl = -kl_weight * dKL_dKp
             gvar_p = gls_p = 0.0
-        gvar, gls, gZ = self._rbf_chain(GU, Kn, D, Z, var, ls)
-        out = {"Z": gZ + self.gZ, "variance": gvar + gvar_p + self.gscal[0], "lengthscale": gls + gls_p + self.gscal[1],
-               "q_mu": g_qmu, "q_sqrt": torch.tril(gLq)}
+        return dict(Z=Z, var=var, ls=ls, q_mu=q_mu, Kn=Kn, D=D, Kinv=Kinv, Kinvb=Kinvb, Bb=Bb, LqbT=stack(Lqb).T.contiguous(),
+                    g_qmu_kl=g_qmu_kl, gLq_kl=gLq_kl, GU_kl=GU_kl, gvar_p=gvar_p, gls_p=gls_p)
+
+    @torch.no_grad()
+    def _m_only_closed_form(self, kl_weight, hyp=None, static=None):
+        """Non-whitened case, written out as ~15 batched GEMMs (no autograd graph, no triangular solves):
+             Q_0 = Kinv, Q_r = B_r B_r^T with B_r = Kinv L_r, beta = Kinv q_mu       (Kinv = Kuu^-1)
+             KL  = 1/2 [q_mu^T Kp^-1 q_mu - MR - sum log diag(L_r)^2 + sum <L_r, Kp^-1 L_r> + R log|Kp|]
+        `static` = the result of m_only_static() for the same parameters (computed here when absent)."""
+        layer = self.layer
+        M, R, Mp = self.M, self.R, self.Mp
+        st = static if static is not None else self.m_only_static(kl_weight, hyp)
+        bt = self.BATCHED_DTYPE
+        gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
+        gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
+        Kinv = st["Kinv"]
+        Ub = (gQ[1:] + gQ[1:].transpose(1, 2)).to(bt) @ st["Bb"]         # d/dB_r
+        gLq = (st["Kinvb"] @ Ub).to(torch.float64) + st["gLq_kl"]        # d/dL_r (through B_r) + KL
+        GK = gQ[0] + (Ub.permute(1, 0, 2).reshape(M, R * M) @ st["LqbT"]).to(torch.float64) + gbeta @ st["q_mu"].T   # d/dKinv
+        g_qmu = Kinv @ gbeta + st["g_qmu_kl"]
+        GU = -(Kinv @ GK @ Kinv)                                         # d/dKuu
+        if st["GU_kl"] is not None:
+            GU = GU + st["GU_kl"]
+        gvar, gls, gZ = self._rbf_chain(GU, st["Kn"], st["D"], st["Z"], st["var"], st["ls"])
+        out = {"Z": gZ + self.gZ, "variance": gvar + st["gvar_p"] + self.gscal[0],
+               "lengthscale": gls + st["gls_p"] + self.gscal[1], "q_mu": g_qmu, "q_sqrt": torch.tril(gLq)}
         if layer._kind == _lib.LAYER_SVGP_CONV:
             out["patch_weights"] = self.gw.clone()
         return out
@@ -461,34 +478,54 @@ class TrainStep(object):
         self.opt = Adam(model, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
         self.opt.bind()
         self.use_graphs = use_graphs
-        self._graphs = [None] * len(model.layers)
-        self._calls = [0] * len(model.layers)
+        self.early_static = os.environ.get("DCGP_EARLY_STATIC", "1") != "0"   # diagnostic switch
+        self._graphs = {"static": {}, "dynamic": {}}
+        self._calls = {"static": {}, "dynamic": {}}
+        self._static = {}
 
-    def _m_only_to_grad(self, i, wsize):
-        """Layer i's M-only chain rule, results stored in its slice of opt.grad (current stream).  ~60 small float64 torch
-        ops with fixed shapes and pointers and no host values: after GRAPH_AFTER eager calls they are replayed as ONE CUDA
-        graph launch (the chain is otherwise bound by host launch overhead)."""
-        eg, opt = self.eg, self.opt
+    def _graphed(self, key, i, fn):
+        """Run fn() on the current stream: eagerly for the first GRAPH_AFTER calls, then captured once and replayed as a
+        single CUDA-graph launch (fixed shapes and pointers, no host values inside)."""
         layer = self.model.layers[i]
+        if not self.use_graphs or layer.white:
+            return fn()
+        g = self._graphs[key].get(i)
+        if g is not None:
+            return g.replay()
+        self._calls[key][i] = self._calls[key].get(i, 0) + 1
+        if self._calls[key][i] <= self.GRAPH_AFTER:
+            return fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=torch.cuda.current_stream(self.model.device), capture_error_mode="thread_local"):
+            fn()
+        self._graphs[key][i] = g
+        g.replay()
+
+    def _m_only_static(self, i, wsize):
+        """Parameter-only part of layer i's chain rule (LayerBackward.m_only_static) on the current stream."""
+        eg, opt = self.eg, self.opt
+        if self.model.layers[i].white:
+            return
 
         def run():
             hyp = torch.nn.functional.softplus(opt.hyp_slice(i)) + 1e-6       # == the values the host holds
+            self._static[i] = eg.bwd[i].m_only_static(kl_weight=1.0 / wsize, hyp=hyp)
+
+        self._graphed("static", i, run)
+
+    def _m_only_to_grad(self, i, wsize):
+        """Layer i's M-only chain rule, results stored in its slice of opt.grad (current stream).  ~40 small torch ops with
+        fixed shapes and pointers and no host values: replayed as ONE CUDA graph launch (the chain is otherwise bound by
+        host launch overhead)."""
+        eg, opt = self.eg, self.opt
+
+        def run():
+            hyp = torch.nn.functional.softplus(opt.hyp_slice(i)) + 1e-6
             grads = [None] * len(self.model.layers)
-            grads[i] = eg.bwd[i].m_only(kl_weight=1.0 / wsize, hyp=hyp)
+            grads[i] = eg.bwd[i].m_only(kl_weight=1.0 / wsize, hyp=hyp, static=self._static.get(i))
             opt._store_grads(grads, i)
 
-        if not self.use_graphs or layer.white:
-            return run()
-        if self._graphs[i] is not None:
-            return self._graphs[i].replay()
-        self._calls[i] += 1
-        if self._calls[i] <= self.GRAPH_AFTER:
-            return run()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=torch.cuda.current_stream(self.model.device), capture_error_mode="thread_local"):
-            run()
-        self._graphs[i] = g
-        g.replay()
+        self._graphed("dynamic", i, run)
 
     def _chain(self, i, wsize):
         """Queue layer i's M-only chain rule + Adam slice on its side stream and leave the rest (hyper-parameter read-back,
@@ -501,6 +538,8 @@ class TrainStep(object):
         done.record(main)
         side.wait_event(done)
         with torch.cuda.stream(side):
+            if not self.early_static:
+                self._m_only_static(i, wsize)
             self._m_only_to_grad(i, wsize)
             host, ev = opt.step_layer(i, None, opt.step_no)
 
@@ -523,6 +562,13 @@ class TrainStep(object):
         _, wsize = world()
         nl = len(model.layers)
         opt.step_no += 1
+        main = torch.cuda.current_stream(model.device)
+        # parameter-only part of every layer's chain rule: queued now on the layers' side streams (behind this step's
+        # prepare), it overlaps the backward pass instead of sitting in the serial tail
+        for i in range(nl if self.early_static else 0):
+            eg._side[i].wait_stream(main)       # (the first step's prepare ran on the model's own side streams)
+            with torch.cuda.stream(eg._side[i]):
+                self._m_only_static(i, wsize)
         # input-gradient path, top to bottom (the first layer has no input gradient: its whole backward runs here)
         for i in range(nl - 1, -1, -1):
             first = (i == 0)
