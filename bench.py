@@ -207,8 +207,20 @@ def run_ours(args, cfg):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
-        dist.init_process_group("nccl", device_id=device)
+        # stdout carries exactly one JSON line: NCCL prints its version banner with printf when the communicator is created
+        # (first collective), so file descriptor 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from deepcgp_b200 import _lib
 
     S, B = cfg["S"], cfg["batch"]
