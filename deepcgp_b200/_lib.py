@@ -67,6 +67,7 @@ SIGNATURES = {
     "dcgp_convkernel_kdiag": (_i, [_pd, _vp, _vp, _i, _vp, _vp]),
     "dcgp_reparameterize": (_i, [_vp, _vp, _vp, _sz, _d, _vp, _vp]),
     "dcgp_multiclass_varexp": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),
+    "dcgp_multiclass_predict": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "dcgp_elbo": (_i, [_vp, _i, _d, _d, _vp, _i, _vp, _vp]),
 }
 

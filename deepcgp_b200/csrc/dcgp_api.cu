@@ -588,6 +588,15 @@ int dcgp_multiclass_varexp(const float* Fmu, const float* Fvar, const int32_t* Y
   return launch_varexp(Fmu, Fvar, Y, S, N, K, epsilon, varexp, sum, (cudaStream_t)stream);
 }
 
+int dcgp_multiclass_predict(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,
+                            double* pmean, double* pvar, double* logdens, void* stream) {
+  if (!Fmu || !Fvar || S < 1 || N < 1 || (!pmean && !pvar && !logdens) || (logdens && !Y)) {
+    set_error("multiclass_predict: bad argument");
+    return DCGP_ERR_ARG;
+  }
+  return launch_multiclass_predict(Fmu, Fvar, Y, S, N, K, epsilon, pmean, pvar, logdens, (cudaStream_t)stream);
+}
+
 int dcgp_elbo(const double* sum_varexp, int S, double num_data, double n_global, const double* kls, int n_layers,
               double* elbo, void* stream) {
   if (!sum_varexp || !kls || !elbo || S < 1 || n_layers < 1 || !(n_global > 0)) { set_error("elbo: bad argument"); return DCGP_ERR_ARG; }

@@ -49,6 +49,8 @@ int launch_elbo(const double* sum_varexp, int S, double scale, const double* kls
 int launch_pack_z(const double* Z, long long n, double inv_ls, float* zs, cudaStream_t st);
 int launch_pack_w(const double* Linv, int ldl, const double* Wr, int M, int Mp, int R, float* W, cudaStream_t st);
 int launch_pack_wmean(const double* beta, int M, int Mp, int R, int RP, float* Wm, cudaStream_t st);
+int launch_multiclass_predict(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,
+                              double* pmean, double* pvar, double* logdens, cudaStream_t st);
 int launch_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon, double coef,
                        float* gmu, float* gvar, cudaStream_t st);
 int launch_sample_backward(const float* gF, const float* z, const float* var, size_t n, float jitter, float* g_mean, float* g_var,

@@ -442,6 +442,43 @@ __global__ void __launch_bounds__(128) varexp_kernel(const float* __restrict__ F
   varexp[i] = p * log1meps + (1.0 - p) * logepsk;
 }
 
+// GPflow MultiClass(RobustMax).predict_mean_and_var / predict_density (the prediction path of DS/dgp.py:116-126): for every
+// class c, p_c = P(f_c is the largest) by the same 20-point quadrature, then ps = p_c (1 - eps) + (1 - p_c) eps/(K-1).
+// One thread per (row, class).  pmean / pvar [SN, K] (var = ps - ps^2) and, when Y is given, logdens[SN] = log ps[y].
+__global__ void __launch_bounds__(128) multiclass_predict_kernel(const float* __restrict__ Fmu, const float* __restrict__ Fvar,
+                                                                 const int32_t* __restrict__ Y, int SN, int N, int K, double eps,
+                                                                 double* __restrict__ pmean, double* __restrict__ pvar,
+                                                                 double* __restrict__ logdens) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= (long long)SN * K) return;
+  const int i = (int)(e / K), c = (int)(e - (long long)i * K);
+  double mu[16], isd[16];
+  for (int k = 0; k < K; ++k) {
+    mu[k] = (double)Fmu[(long long)i * K + k];
+    const double v = fmax((double)Fvar[(long long)i * K + k], 1e-10);
+    isd[k] = 1.0 / sqrt(v);
+  }
+  const double mu_c = mu[c];
+  const double sd2 = sqrt(fmax(2.0 * (double)Fvar[(long long)i * K + c], 1e-10));
+  double p = 0.0;
+  for (int g = 0; g < 20; ++g) {
+    const double x = mu_c + c_gh_x[g] * sd2;
+    double prod = 1.0;
+    for (int k = 0; k < K; ++k) {
+      if (k == c) continue;
+      const double dist = (x - mu[k]) * isd[k];
+      double cdf = 0.5 * (1.0 + erf(dist * 0.70710678118654752440));
+      cdf = cdf * (1.0 - 2e-4) + 1e-4;
+      prod *= cdf;
+    }
+    p += prod * c_gh_w[g];
+  }
+  const double ps = p * (1.0 - eps) + (1.0 - p) * (eps / (K - 1.0));
+  if (pmean) pmean[e] = ps;
+  if (pvar) pvar[e] = ps - ps * ps;
+  if (logdens && Y && Y[i % N] == c) logdens[i] = log(ps);
+}
+
 __global__ void __launch_bounds__(1024) sum_f64_kernel(const double* __restrict__ x, int n, double* __restrict__ out) {
   __shared__ double sh[32];
   double v = 0.0;
@@ -611,6 +648,15 @@ int launch_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, 
   varexp_kernel<<<ceil_div(SN, 128), 128, 0, st>>>(Fmu, Fvar, Y, SN, N, K, log(1.0 - epsilon), log(epsilon / (K - 1.0)), varexp);
   sum_f64_kernel<<<1, 1024, 0, st>>>(varexp, SN, sum);
   return check_launch("varexp", 2);
+}
+
+int launch_multiclass_predict(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,
+                              double* pmean, double* pvar, double* logdens, cudaStream_t st) {
+  if (K > 16 || K < 2) { set_error("multiclass_predict: K must be in [2,16]"); return DCGP_ERR_ARG; }
+  init_gh();
+  const long long n = (long long)S * N * K;
+  multiclass_predict_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Fmu, Fvar, Y, S * N, N, K, epsilon, pmean, pvar, logdens);
+  return check_launch("multiclass_predict");
 }
 
 __global__ void elbo_kernel(const double* sum_varexp, int S, double scale, const double* kls, int n_layers, double* elbo) {

@@ -113,6 +113,26 @@ class DGP_Base(object):
                                       _lib.ptr(self._kls), len(self.layers), _lib.ptr(self._elbo), _lib.stream()))
         return self._elbo[0]
 
+    # ------------------------------------------------------------------ DS/dgp.py:100-126 (autoflow methods)
+    def predict_f(self, Xnew, num_samples, zs=None):
+        """(Fmean, Fvar) of the last layer, each [S, N, K]."""
+        return self._build_predict(Xnew, full_cov=False, S=int(num_samples), zs=zs)
+
+    def predict_all_layers(self, Xnew, num_samples, zs=None):
+        return self.propagate(Xnew, full_cov=False, S=int(num_samples), zs=zs)
+
+    def predict_y(self, Xnew, num_samples, zs=None):
+        """DS/dgp.py:116-119: class probabilities and their variance per sample, each [S, N, K] (float64)."""
+        Fmean, Fvar = self._build_predict(Xnew, full_cov=False, S=int(num_samples), zs=zs)
+        return self.likelihood.predict_mean_and_var(Fmean, Fvar)
+
+    def predict_density(self, Xnew, Ynew, num_samples, zs=None):
+        """DS/dgp.py:121-126: log (1/S) sum_s p(y | f_s) -> [N, 1]."""
+        S = int(num_samples)
+        Fmean, Fvar = self._build_predict(Xnew, full_cov=False, S=S, zs=zs)
+        l = self.likelihood.predict_density(Fmean, Fvar, Ynew)
+        return torch.logsumexp(l - float(np.log(S)), dim=0)
+
     def compute_log_likelihood(self, X=None, Y=None, zs=None):
         """GPflow Model.compute_log_likelihood: the ELBO as a Python float (synchronises; raises on a failed Cholesky)."""
         elbo = self._build_likelihood(X, Y, zs)

@@ -192,6 +192,12 @@ int dcgp_reparameterize(const float* mean, const float* var, const float* z, siz
  * varexp (DS/dgp.py:90,94 take mean over S then sum over N: divide by S on the host side). */
 int dcgp_multiclass_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K,
                            double epsilon, double* varexp, double* sum, void* stream);
+/* Prediction path (DS/dgp.py:116-126 predict_y / predict_density -> DS/utils.py:107-121 -> GPflow MultiClass(RobustMax)
+ * predict_mean_and_var / predict_density): pmean[SN, K] = p_c (1-eps) + (1-p_c) eps/(K-1) with p_c = P(f_c largest) by the
+ * same 20-point quadrature, pvar = pmean - pmean^2, logdens[SN] = log pmean[., Y] (any of the three may be NULL; Y [N]
+ * is only read for logdens).  float64 outputs. */
+int dcgp_multiclass_predict(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,
+                            double* pmean, double* pvar, double* logdens, void* stream);
 
 /* DS/dgp.py:92-98 _build_likelihood: elbo = sum_varexp/S * (num_data/N_global) - sum_l KL_l   (device doubles) */
 int dcgp_elbo(const double* sum_varexp, int S, double num_data, double n_global, const double* kls,

@@ -291,6 +291,41 @@ def robustmax_varexp(Fmu, Fvar, Y, num_classes=10, epsilon=1e-3, n_gh=20):
     return p * np.log(1.0 - epsilon) + (1.0 - p) * np.log(epsilon / (num_classes - 1.0))
 
 
+def robustmax_predict(Fmu, Fvar, num_classes=10, epsilon=1e-3, n_gh=20):
+    """GPflow-1.2.0 MultiClass(RobustMax).predict_mean_and_var: ps [n,K] = p_c (1-eps) + (1-p_c) eps/(K-1), and ps - ps^2."""
+    gh_x, gh_w = np.polynomial.hermite.hermgauss(n_gh)
+    n = Fmu.shape[0]
+    sd = np.sqrt(np.clip(Fvar, 1e-10, np.inf))
+    ps = np.empty((n, num_classes))
+    for c in range(num_classes):
+        X = Fmu[:, c:c + 1] + gh_x[None, :] * np.sqrt(np.clip(2.0 * Fvar[:, c], 1e-10, np.inf))[:, None]
+        cdfs = 0.5 * (1.0 + ssp.erf((X[:, None, :] - Fmu[:, :, None]) / sd[:, :, None] / np.sqrt(2.0)))
+        cdfs = cdfs * (1 - 2e-4) + 1e-4
+        cdfs[:, c, :] = 1.0
+        p = np.prod(cdfs, axis=1) @ (gh_w / np.sqrt(np.pi))
+        ps[:, c] = p * (1.0 - epsilon) + (1.0 - p) * (epsilon / (num_classes - 1.0))
+    return ps, ps - ps * ps
+
+
+def dgp_predict_y(layers, X, zs, S, jitter=JITTER, fast=False):
+    """DGP_Base.predict_y (DS/dgp.py:116-119) with explicit samples zs -> (mean, var), each [S,N,K]."""
+    N = X.shape[0]
+    _, Fmeans, Fvars = propagate(layers, X, S, zs, jitter, fast)
+    K = Fmeans[-1].shape[2]
+    m, v = robustmax_predict(Fmeans[-1].reshape(S * N, K), Fvars[-1].reshape(S * N, K), K)
+    return m.reshape(S, N, K), v.reshape(S, N, K)
+
+
+def dgp_predict_density(layers, X, Y, zs, S, jitter=JITTER, fast=False):
+    """DGP_Base.predict_density (DS/dgp.py:121-126) -> [N,1]."""
+    N = X.shape[0]
+    m, _ = dgp_predict_y(layers, X, zs, S, jitter, fast)
+    y = np.asarray(Y).astype(np.int64).reshape(-1)
+    l = np.log(m[:, np.arange(N), y])                                     # [S,N]
+    mx = l.max(axis=0)
+    return (mx + np.log(np.exp(l - mx).sum(axis=0)) - np.log(float(S)))[:, None]
+
+
 def dgp_elbo(layers, X, Y, zs, num_data, S, jitter=JITTER, fast=False):
     """DGP_Base._build_likelihood (DS/dgp.py:83-98) with BroadcastingLikelihood (DS/utils.py:71-93)."""
     N = X.shape[0]

@@ -385,6 +385,12 @@ class MultiClass(Likelihood):
         ps = _np.concatenate(ps, axis=1)
         return _t(ps), _t(ps - _np.square(ps))
 
+    def predict_density(self, Fmu, Fvar, Y):
+        gh_x, gh_w = _np.polynomial.hermite.hermgauss(self.num_gauss_hermite_points)
+        p = self.invlink.prob_is_largest(Y, Fmu, Fvar, gh_x, gh_w)
+        eps = float(self.invlink.epsilon)
+        return _t(_np.log(p * (1.0 - eps) + (1.0 - p) * self.invlink._eps_K1))
+
 
 likelihoods.Likelihood = Likelihood
 likelihoods.Gaussian = Gaussian

@@ -153,8 +153,13 @@ def case_dgp(name, seed, N, S, num_data, H, W, C, conv_specs, last_spec, white=F
     Fs, Fmeans, Fvars = model.propagate(tf.constant(X), full_cov=False, S=S, zs=[tf.constant(z) for z in zs])
     L = tf.reduce_sum(model.likelihood.variational_expectations(Fmeans[-1], Fvars[-1], model.Y))
     KLs = [lay.KL() for lay in layers]
+    # prediction path (DS/dgp.py:116-126) on the same samples: BroadcastingLikelihood.predict_mean_and_var / predict_density
+    pmean, pvar = model.likelihood.predict_mean_and_var(Fmeans[-1], Fvars[-1])
+    pdens = model.likelihood.predict_density(Fmeans[-1], Fvars[-1], model.Y)
+    logdens = tf.reduce_logsumexp(pdens - np.log(float(S)), axis=0)
     arrs = dict(X=X, Y=Y, S=S, num_data=num_data, n_layers=len(layers), elbo=elbo, KLs=np.array(KLs),
                 varexp=model.likelihood.variational_expectations(Fmeans[-1], Fvars[-1], model.Y),
+                pred_mean=pmean, pred_var=pvar, pred_density=pdens, pred_logdensity=logdens,
                 jitter=gpflow.settings.jitter)
     for i, (m, z) in enumerate(zip(metas, zs)):
         arrs.update(flat("l%d_" % i, m))

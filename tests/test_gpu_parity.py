@@ -96,7 +96,7 @@ def test_kuu_kuf(name):
 
 
 # ----------------------------------------------------------------------------------------------- K-C
-@pytest.mark.parametrize("M", [1, 17, 64, 200, 512])
+@pytest.mark.parametrize("M", [1, 17, 64, 65, 129, 200, 512, 1024])
 def test_cholesky(M):
     from deepcgp_b200 import _lib
     rng = np.random.RandomState(M)
@@ -211,6 +211,30 @@ def test_dgp_elbo_vs_golden(name, algo):
     np.testing.assert_allclose(npy(model._kls), g["KLs"], rtol=KL_RTOL[algo])
     ve = model.likelihood.variational_expectations(Fmeans[-1], Fvars[-1], g["Y"])
     np.testing.assert_allclose(npy(ve), g["varexp"], rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("name", golden_names("dgp"))
+def test_prediction_path_vs_golden(name):
+    """predict_y / predict_density (DS/dgp.py:116-126) against the reference's BroadcastingLikelihood on the golden samples."""
+    g = load_golden(name)
+    layers = layers_from_golden(g)
+    S = int(g["S"])
+    X32 = g["X"].astype(np.float32)
+    model = build_model(layers, X32, g["Y"], S, float(g["num_data"]), "tc")
+    zs = [torch.as_tensor(g["z%d" % i].astype(np.float32), device=dev()) for i in range(len(layers))]
+    pm, pv = model.predict_y(X32, S, zs=zs)
+    assert tuple(pm.shape) == g["pred_mean"].shape
+    np.testing.assert_allclose(npy(pm), g["pred_mean"], rtol=2e-3, atol=2e-5)
+    np.testing.assert_allclose(npy(pv), g["pred_var"], rtol=2e-3, atol=2e-5)
+    ld = model.predict_density(X32, g["Y"], S, zs=zs)
+    np.testing.assert_allclose(npy(ld), g["pred_logdensity"], rtol=1e-3, atol=1e-4)
+    # the likelihood kernel alone, on the golden (float64) inputs rounded to float32
+    Fm = torch.as_tensor(g["Fmean%d" % (len(layers) - 1)].astype(np.float32), device=dev())
+    Fv = torch.as_tensor(g["Fvar%d" % (len(layers) - 1)].astype(np.float32), device=dev())
+    m2, v2 = model.likelihood.predict_mean_and_var(Fm, Fv)
+    np.testing.assert_allclose(npy(m2), g["pred_mean"], rtol=1e-4, atol=1e-6)
+    d2 = model.likelihood.predict_density(Fm, Fv, g["Y"])
+    np.testing.assert_allclose(npy(d2), g["pred_density"], rtol=1e-4, atol=1e-5)
 
 
 def test_varexp_matches_oracle_on_random_inputs():

@@ -69,6 +69,21 @@ def test_dgp_elbo(name):
     np.testing.assert_allclose(elbo_fast, g["elbo"], rtol=1e-9)
 
 
+@pytest.mark.parametrize("name", golden_names("dgp"))
+def test_dgp_prediction_path(name):
+    """DS/dgp.py:116-126 predict_y / predict_density on the golden samples (BroadcastingLikelihood from the reference source)."""
+    g = load_golden(name)
+    layers = layers_from_golden(g)
+    S, jit = int(g["S"]), float(g["jitter"])
+    zs = [g["z%d" % i] for i in range(len(layers))]
+    m, v = O.dgp_predict_y(layers, g["X"], zs, S, jit)
+    np.testing.assert_allclose(m, g["pred_mean"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(v, g["pred_var"], rtol=1e-9, atol=1e-12)
+    ld = O.dgp_predict_density(layers, g["X"], g["Y"], zs, S, jit)
+    np.testing.assert_allclose(ld, g["pred_logdensity"], rtol=1e-9)
+    assert np.all(m > 0) and np.all(m.sum(-1) < 1.0 + 1e-9)
+
+
 # ----------------------------------------------------------------------------- App. A.6 self-checks
 def _rand_layer(rng, H=7, W=7, C=2, f=3, s=1, M=9, R=3, white=False):
     L = f * f * C
