@@ -338,13 +338,14 @@ def run_ours(args, cfg):
 
 
 def kernel_roofline(model, cfg, B, S, device, flush):
-    """Dominant kernel = the tcgen05 conditional GEMM `tc_kernel<MODE_COND,256>` of conv layer 2 (forward); the two big
+    """Dominant kernel = the tcgen05 conditional GEMM of conv layer 2 (forward) -- since the chained form two launches of
+    the same kernel, `tc_kernel<MODE_A,256>` (a = K Lm^-T) + `tc_kernel<MODE_COND,256>` (G_r = a C_r), timed together; the two big
     backward GEMMs of the same layer (`dk_gemm_kernel`, `xf_gemm_kernel`) and the Kuf kernel are reported next to it.
     Every kernel is timed live with CUDA events recorded by the library on the launching stream around that launch
     (dcgp_set_kernel_timing), L2 flushed before every repetition.
       achieved = ALGORITHMIC flops per launch (T*(M^2 + R*M^2 + 2MR + 2M(R+1)), triangular count, no split)
                  / launch duration;   peak = MEASURED_PEAKS.json bf16 burst (the kernel is timed alone);
-      executed_* = the tensor-pipe flops the launch really issues: 3 split products x dense operands;
+      executed_* = the tensor-pipe flops the launch really issues: 3 split products x the k-blocks not skipped as zero;
       traffic = dram__bytes_read + dram__bytes_write of this launch from the committed `ncu --set full` capture
                 (profiles/r1b_ncu_full_layer2.csv)."""
     import torch
@@ -390,7 +391,8 @@ def kernel_roofline(model, cfg, B, S, device, flush):
     M, R, P, L = layer.num_inducing, layer.gp_count, layer.patch_count, layer.patch_length
     T = P * n_rows
     alg = T * (M * M + R * M * M + 2.0 * M * R + 2.0 * M * (R + 1))
-    executed = 3 * 2.0 * T * ((R + 1) * M * M + 256 * M)
+    chained = os.environ.get("DCGP_FWD_CHAINED", "1") != "0"     # two triangular stages: 3/4 of the k-blocks of each tile
+    executed = 3 * 2.0 * T * ((0.75 if chained else 1.0) * (R + 1) * M * M + 256 * M)
     ach = alg / (ms * 1e-3) / 1e12
     kuf_bytes = 4.0 * T * M + 4.0 * n_rows * D_in            # K planes written (hi+lo fp16) + images read
     kuf_flops = 3 * 2.0 * T * M * 256                        # 3 split products over the padded patch length
@@ -412,7 +414,8 @@ def kernel_roofline(model, cfg, B, S, device, flush):
     dq = tensor_entry("xf_gemm_kernel<256> (dQ GEMM, in-smem column rescale, conv layer 2 backward)", ms_dq,
                       1.0 * T * R * M * M, 3 * 2.0 * T * R * M * M * 0.75,
                       {"traffic": 790946688, "tensor_pipe_active_pct_ncu": 60.7})
-    return {"bound": "tensor", "kernel": "tc_kernel<MODE_COND,256> (conditional GEMM, conv layer 2 forward)",
+    return {"bound": "tensor", "kernel": "tc_kernel<MODE_A,256> + tc_kernel<MODE_COND,256> (chained conditional GEMM, conv layer 2 "
+                                         "forward)" if chained else "tc_kernel<MODE_COND,256> (conditional GEMM, conv layer 2 forward)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
             "traffic": 877827921, "ms": ms, "algorithmic_gflop": alg / 1e9,
             "executed_tensor_gflop": executed / 1e9, "executed_tflops": executed / (ms * 1e-3) / 1e12,

@@ -58,7 +58,7 @@ static Prep carve_prep(const dcgp_layer_desc* d, void* buf) {
 
 struct F64Work {
   int M, Mq, R;
-  double *Kuu, *invD, *Linv, *Kinv, *Wr, *beta, *Lpinv, *invDp, *tmpMR, *tmpK, *sc;
+  double *Kuu, *invD, *Linv, *Kinv, *Wr, *beta, *alpha, *Lpinv, *invDp, *tmpMR, *tmpK, *sc;
   void *trws, *trws2;
   size_t bytes;
 };
@@ -82,6 +82,7 @@ static F64Work carve_f64(int M, int R, void* ws) {
   w.tmpMR = c.take<double>((size_t)M * R);
   w.tmpK = c.take<double>((size_t)M * M);
   w.sc = c.take<double>(8);
+  w.alpha = c.take<double>((size_t)M * R);     // Lm^-1 q_mu: mean operand of the chained conditional
   w.bytes = align_up(c.off, 256);
   return w;
 }
@@ -365,13 +366,24 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
     }
     // forward operands first; the caller's event marks the point from which dcgp_layer_apply may run -- the KL (which
     // joins the prior chain) and the backward operands follow on the same stream, off the forward's critical path
+    const int chained = (d->kind == DCGP_LAYER_CONV && tc_forward_chained()) ? 1 : 0;
+    const double* alpha = q_mu;          // whitened: mean = a^T q_mu
+    if (chained && !d->white) {          // alpha = Lm^-1 q_mu
+      GemmF64 g{};
+      g.m = M; g.n = R; g.k = M;
+      g.A = w.Linv; g.lda = w.Mq; g.lowerA = 1;
+      g.B = q_mu; g.ldb = R;
+      g.C = w.alpha; g.ldc = R; g.alpha = 1.0; g.batch = 1;
+      DCGP_TRY(gemm_f64(g, st));
+      alpha = w.alpha;
+    }
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, 1, st));
+                               w.beta, w.sc + 1, w.Kinv, 1, chained, alpha, st));
     DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
     if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
     if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, 2, st));
+                               w.beta, w.sc + 1, w.Kinv, 2, chained, alpha, st));
     return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
   }
   if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);

@@ -151,6 +151,8 @@ struct CondCfg {
 
 constexpr int MODE_COND = 0;   // conditional GEMM: per-row-block sums of squares + mean rows
 constexpr int MODE_GEMM = 1;   // plain batched C = A * B^T: store fp32 and/or accumulate the sum of squares of C
+constexpr int MODE_A = 2;      // chained form, first stage: a = K Lm^-T (lower-triangular operand: zero k-blocks skipped),
+                               // acc[t, 0] = |a_t|^2 and the split-fp16 planes of a for the second stage
 
 struct TcParams {
   int n_items;
@@ -165,6 +167,10 @@ struct TcParams {
   const float* kscal;  // device: [0]=K scale, [1]=1/K scale
   float* acc;     // [T, R+1]
   float* mean;    // [T, R]
+  int blk_first;  // MODE_COND: first W block of an item (1 when block 0 was done by the MODE_A stage)
+  int tri;        // MODE_COND: 2 = the W blocks are upper triangular (C_r^T): k-blocks below the tile's first row are skipped
+  __half* Ah_out; __half* Al_out;   // MODE_A: planes of a [Tpad, Mp]
+  const float* ascal;               // MODE_A: {scale, 1/scale} of those planes
   // ---- MODE_GEMM: C[b][i, j] = sum_k A[b*a_batch_rows + i, k] * B[b*b_batch_rows + j, k]
   int m_tiles, n_tiles;
   int a_batch_rows, b_batch_rows;
@@ -183,15 +189,20 @@ struct TcParams {
 
 template <int MODE, int BN>
 __device__ __forceinline__ int tiles_in_item(const TcParams& p, int item) {
-  if (MODE == MODE_COND) return (item % (p.R + 2) == p.R + 1) ? 1 : p.njt;
+  if (MODE == MODE_COND) { const int per = p.R + 2 - p.blk_first; return (item % per == per - 1) ? 1 : p.njt; }
+  if (MODE == MODE_A) return p.njt;
   return 1;
 }
 template <int MODE, int BN>
 __device__ __forceinline__ void tile_rows(const TcParams& p, int item, int jt, int& a_row, int& b_row) {
   if (MODE == MODE_COND) {
-    const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
+    const int per = p.R + 2 - p.blk_first;
+    const int tt = item / per, blk = p.blk_first + item - tt * per;
     a_row = tt * kBM;
     b_row = blk * p.Mp + jt * BN;
+  } else if (MODE == MODE_A) {
+    a_row = item * kBM;
+    b_row = jt * BN;
   } else {
     const int per = p.m_tiles * p.n_tiles;
     const int bb = item / per, rem = item - bb * per;
@@ -202,9 +213,14 @@ __device__ __forceinline__ void tile_rows(const TcParams& p, int item, int jt, i
   }
 }
 // k-block range of an item (split-K for MODE_GEMM)
-template <int MODE>
-__device__ __forceinline__ void item_krange(const TcParams& p, int item, int& kb0, int& kb1) {
+template <int MODE, int BN>
+__device__ __forceinline__ void item_krange(const TcParams& p, int item, int jt, int& kb0, int& kb1) {
   kb0 = 0; kb1 = p.nkb;
+  if (MODE == MODE_A) kb1 = min(p.nkb, ((jt + 1) * BN + kBK - 1) / kBK);          // Lm^-1[j, m] = 0 for m > j
+  if (MODE == MODE_COND && p.tri == 2) {
+    const int per = p.R + 2 - p.blk_first;
+    if (item % per != per - 1) kb0 = (jt * BN) / kBK;                              // C_r^T[j, i] = 0 for i < j
+  }
   if (MODE == MODE_GEMM && p.splits > 1) {
     const int per = p.m_tiles * p.n_tiles;
     const int nbatch = p.n_items / per / p.splits;
@@ -252,7 +268,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         for (int jt = 0; jt < njt; ++jt) {
           int arow, brow, kb0, kb1;
           tile_rows<MODE, BN>(p, item, jt, arow, brow);
-          item_krange<MODE>(p, item, kb0, kb1);
+          item_krange<MODE, BN>(p, item, jt, kb0, kb1);
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
@@ -280,7 +296,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           int kb0, kb1;
-          item_krange<MODE>(p, item, kb0, kb1);
+          item_krange<MODE, BN>(p, item, jt, kb0, kb1);
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
@@ -314,8 +330,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       const float inv_w = p.wscal[1], inv_wm = p.wscal[3], inv_k = p.kscal[1];
       const float sq_scale = (inv_w * inv_k) * (inv_w * inv_k);
       const float mean_scale = inv_wm * inv_k;
+      const int per = p.R + 2 - p.blk_first;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int tt = item / (p.R + 2), blk = item - tt * (p.R + 2);
+        const int tt = item / per, blk = p.blk_first + item - tt * per;
         const bool is_mean = (blk == p.R + 1);
         const int njt = is_mean ? 1 : p.njt;
         const int t = tt * kBM + q * 32 + lane;
@@ -359,6 +376,45 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           mbar_arrive(&tmem_empty[buf]);
         }
         if (!is_mean && t < p.T) p.acc[(long long)t * (p.R + 1) + blk] = ssq * sq_scale;
+      }
+    } else if (MODE == MODE_A) {
+      const float inv = p.wscal[1] * p.kscal[1];               // accumulator -> a
+      const float sa = p.ascal[0];
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const long long t = (long long)item * kBM + q * 32 + lane;   // < Tpad: padding rows hold zeros (K rows are zero)
+        float ssq = 0.f;
+        for (int jt = 0; jt < p.njt; ++jt, ++tile) {
+          const uint32_t buf = tile & 1, use = tile >> 1;
+          mbar_wait(&tmem_full[buf], use & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + lane_base + buf * BN;
+          __half* oh = p.Ah_out + t * p.Mp + jt * BN;
+          __half* ol = p.Al_out + t * p.Mp + jt * BN;
+#pragma unroll 1
+          for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            tmem_ld_32x32(taddr + c, v);
+            __align__(16) __half2 hi[16];
+            __align__(16) __half2 lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a0 = v[2 * i] * inv, a1 = v[2 * i + 1] * inv;
+              ssq = fmaf(a0, a0, fmaf(a1, a1, ssq));
+              const float s0 = a0 * sa, s1 = a1 * sa;
+              hi[i] = __floats2half2_rn(s0, s1);
+              const float2 hf = __half22float2(hi[i]);
+              lo[i] = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              reinterpret_cast<uint4*>(oh + c)[i] = reinterpret_cast<uint4*>(hi)[i];
+              reinterpret_cast<uint4*>(ol + c)[i] = reinterpret_cast<uint4*>(lo)[i];
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        if (t < p.T) p.acc[t * (p.R + 1)] = ssq;
       }
     } else {
       const float inv = p.a_scal[1] * p.b_scal[1];
@@ -525,6 +581,53 @@ static int launch_cond_tc(const TcPrep& prep, const TcCondWork& w, int T, int Mp
   p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
   ScopedTimer timer(0, st);
   return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, p, st);
+}
+
+__global__ void set_scale_kernel(float bound, float* __restrict__ scal2);
+
+bool tc_forward_chained() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("DCGP_FWD_CHAINED"); v = (e && atoi(e) == 0) ? 0 : 1; }
+  return v != 0;
+}
+
+// Chained conditional (conditionals.py:31-65 as two triangular GEMMs instead of one dense stack):
+//   stage 1 (MODE_A):   a = K Lm^-T         -> acc[:, 0] = |a|^2, planes of a        (Lm^-1 lower triangular: 3/4 of the k-blocks)
+//   stage 2 (MODE_COND) G_r = a C_r, mean   -> acc[:, r] = |G_r|^2, mean             (C_r^T upper triangular: 3/4 of the k-blocks)
+// |a|^2 <= k(x, x) (the conditional variance is non-negative), so sqrt(a_bound) bounds every entry of a: data-independent scale.
+template <int BN>
+static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc,
+                               float* mean, cudaStream_t st) {
+  CUtensorMap tmKh, tmKl, tmAh, tmAl, tmBh, tmBl;
+  int rc;
+  if ((rc = make_tmap_f16(&tmKh, w.Kh, w.Tpad, Mp, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmKl, w.Kl, w.Tpad, Mp, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmAh, w.Ah, w.Tpad, Mp, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmAl, w.Al, w.Tpad, Mp, kBM))) return rc;
+  if ((rc = make_tmap_f16(&tmBh, prep.Wh, w_rows(Mp, R), Mp, BN))) return rc;
+  if ((rc = make_tmap_f16(&tmBl, prep.Wl, w_rows(Mp, R), Mp, BN))) return rc;
+  set_scale_kernel<<<1, 1, 0, st>>>(sqrtf(a_bound), w.ascal);
+  if ((rc = check_launch("set_scale"))) return rc;
+  ScopedTimer timer(0, st);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.Mp = Mp; p.R = R; p.njt = Mp / BN; p.nkb = Mp / kBK;
+  p.n_items = ceil_div(T, kBM);
+  p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
+  p.Ah_out = (__half*)w.Ah; p.Al_out = (__half*)w.Al; p.ascal = w.ascal;
+  if ((rc = launch_tc<MODE_A, BN>(tmKh, tmKl, tmBh, tmBl, p, st))) return rc;
+  p.n_items = ceil_div(T, kBM) * (R + 1);
+  p.blk_first = 1; p.tri = 2; p.kscal = w.ascal;
+  return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, p, st);
+}
+
+int tc_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc, float* mean,
+                    cudaStream_t st) {
+  if (R > 64) { set_error("tc_cond: R > 64 unsupported"); return DCGP_ERR_ARG; }
+  if (!w.Ah) { set_error("tc_cond_chained: no workspace for the a planes"); return DCGP_ERR_ARG; }
+  if (Mp % 256 == 0) return launch_cond_chained<256>(prep, w, T, Mp, R, a_bound, acc, mean, st);
+  if (Mp % 128 == 0) return launch_cond_chained<128>(prep, w, T, Mp, R, a_bound, acc, mean, st);
+  return launch_cond_chained<64>(prep, w, T, Mp, R, a_bound, acc, mean, st);
 }
 
 // Batched C[b] = A[b] * B[b]^T on split-fp16 planes (both K-major, row-stacked batches); rows/K padded by the caller.
@@ -817,46 +920,80 @@ int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double*
   return check_launch("tc_pack_operands", 2);
 }
 
+// Wr32[(r*Mp + j)*Mp + i] = L_r[i, j] (i >= j), 0 elsewhere: C_r^T for the whitened chained conditional
+__global__ void qsqrt_t_f32_kernel(const double* __restrict__ q_sqrt, int M, int Mp, int R, float* __restrict__ out) {
+  const long long total = (long long)R * Mp * Mp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e % Mp);
+    const long long q = e / Mp;
+    const int j = (int)(q % Mp), r = (int)(q / Mp);
+    out[e] = (i < M && j < M && i >= j) ? (float)q_sqrt[((long long)r * M + i) * M + j] : 0.f;
+  }
+}
+
 // Tensor-core build of the R-batched M-only products (the O(R M^3) part of the step's minibatch-independent work):
 //   W_r = L_r^T G            (G = Kuu^-1 symmetric, or Lm^-1 when whitened)                -> fp32, then the W planes
 //   trace = sum_r |Lp^-1 L_r|_F^2   (GPflow gauss_kl / DS/layers.py:250)                  -> *trace_out (double)
 // Linv/G/Lpinv/beta are float64 (Cholesky-quality); only these products run split-fp16 on tcgen05.
 int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
                       const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out,
-                      const double* Kinv, int parts, cudaStream_t st) {
+                      const double* Kinv, int parts, int chained, const double* alpha, cudaStream_t st) {
   const int M = t.M, Mp = t.Mp, R = t.R;
   int rc;
   if (parts & 1) {
     // ---- part 1: what the forward conditional GEMM needs (W planes)
     cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
     if ((rc = maxabs_f64(q_sqrt, (long long)R * M, M, M, M, t.mx + 2, st))) return rc;
-    if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc;
-    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 2, 2, t.scal);
+    if (!chained) { if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc; }
+    else if (!g_is_linv) { if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 4, st))) return rc; }
+    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 2, 3, t.scal);
     check_launch("scales_from_max");
     // QT[r*Mp + i, k] = L_r[k, i]  (transpose of the lower-triangular q_sqrt_r)
     if ((rc = pack_planes_f64(q_sqrt, M, (long long)M * M, M, M, 1, 1, R, Mp, Mp, t.scal + 4, t.QTh, t.QTl, st))) return rc;
-    // B operand of W_r: B[j, k] = G[k, j]  (G symmetric when it is Kuu^-1; the transpose of Lm^-1 when whitened)
-    if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
-    TcGemm g;
-    memset(&g, 0, sizeof(g));
-    g.Ah = t.QTh; g.Al = t.QTl; g.a_rows_total = (long long)R * Mp; g.a_batch_rows = Mp;
-    g.Bh = t.Gh; g.Bl = t.Gl; g.b_rows_total = Mp; g.b_batch_rows = 0;
-    g.batch = R; g.m = M; g.n = M; g.m_pad = Mp; g.n_pad = Mp; g.k_pad = Mp;
-    g.a_scal = t.scal + 4; g.b_scal = t.scal + 6;
-    g.C = t.Wr32; g.c_batch_stride = (long long)Mp * Mp; g.ldc = Mp;
     if (M != Mp) cudaMemsetAsync(t.Wr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);   // padding must not poison the max scan
-    if ((rc = tc_gemm(g, st))) return rc;
-    // W planes for the conditional GEMM: block 0 = Lm^-1 (float64), blocks 1..R = W_r (fp32 product), mean rows = beta^T
+    if (chained && g_is_linv) {
+      // whitened: C_r = L_r, so the stage-2 operand C_r^T is just the transposed q_sqrt
+      qsqrt_t_f32_kernel<<<num_sms() * 8, 256, 0, st>>>(q_sqrt, M, Mp, R, t.Wr32);
+      if ((rc = check_launch("qsqrt_t"))) return rc;
+    } else {
+      TcGemm g;
+      memset(&g, 0, sizeof(g));
+      g.Ah = t.QTh; g.Al = t.QTl; g.a_rows_total = (long long)R * Mp; g.a_batch_rows = Mp;
+      if (!chained) {
+        // W_r = L_r^T G.  B operand: B[j, k] = G[k, j]  (G symmetric when it is Kuu^-1; the transpose of Lm^-1 when whitened)
+        if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
+        g.Bh = t.Gh; g.Bl = t.Gl; g.b_scal = t.scal + 6;
+      } else {
+        // C_r^T = L_r^T Lm^-T:  C[(r,j), i] = sum_k L_r[k, j] Lm^-1[i, k].  B operand: the rows of Lm^-1 (in the Lp planes,
+        // which part 2 re-packs with the prior's Lp^-1 afterwards)
+        if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 8, t.Lph, t.Lpl, st))) return rc;
+        g.Bh = t.Lph; g.Bl = t.Lpl; g.b_scal = t.scal + 8;
+      }
+      g.b_rows_total = Mp; g.b_batch_rows = 0;
+      g.batch = R; g.m = M; g.n = M; g.m_pad = Mp; g.n_pad = Mp; g.k_pad = Mp;
+      g.a_scal = t.scal + 4;
+      g.C = t.Wr32; g.c_batch_stride = (long long)Mp * Mp; g.ldc = Mp;
+      if ((rc = tc_gemm(g, st))) return rc;
+    }
+    // W planes for the conditional GEMM: block 0 = Lm^-1 (float64), blocks 1..R = W_r or C_r^T (fp32 product), mean rows =
+    // beta^T or alpha^T
+    const double* mvec = chained ? alpha : beta;
     if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 0, st))) return rc;
     if ((rc = maxabs_f32(t.Wr32, (long long)R * Mp * Mp, t.mx + 0, st))) return rc;
-    if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 1, st))) return rc;
+    if ((rc = maxabs_f64(mvec, M, R, R, 0, t.mx + 1, st))) return rc;
     scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
-    pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
+    pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, mvec, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
                                                      (__half*)t.Wh, (__half*)t.Wl);
     if ((rc = check_launch("tc_build_operands", 2))) return rc;
   }
   if (!(parts & 2)) return DCGP_OK;
   // ---- part 2: KL trace and the backward operands (not needed by the forward conditional)
+  if (chained) {   // the G planes (A operand of B_r = G L_r below) were not needed by part 1
+    if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc;
+    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 3, 1, t.scal);
+    if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
+    cudaMemsetAsync(t.mx + 4, 0, sizeof(float), st);
+  }
   if (Lpinv) {
     if ((rc = maxabs_f64(Lpinv, M, M, ldp, 0, t.mx + 4, st))) return rc;
     scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 4, 1, t.scal);
@@ -1252,6 +1389,11 @@ void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_
   a.kk.Kh = c.take(a.kk.Tpad * Mp * 2);
   a.kk.Kl = c.take(a.kk.Tpad * Mp * 2);
   a.kk.kscal = (float*)c.take(8 * 4);
+  if (kind == DCGP_LAYER_CONV) {   // planes of a = Lm^-1 k for the chained conditional
+    a.kk.Ah = c.take(a.kk.Tpad * Mp * 2);
+    a.kk.Al = c.take(a.kk.Tpad * Mp * 2);
+    a.kk.ascal = (float*)c.take(8 * 4);
+  }
   if (kind != DCGP_LAYER_CONV) {
     a.kz.Tpad = align_up(T, kBM);
     a.kz.Kh = c.take(a.kz.Tpad * Mp * 2);
@@ -1274,7 +1416,10 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
   check_launch("set_scale");
   int rc = tc_kuf(prep, v, X, n_rows, variance, inv_ls, a.kk.kscal, a.kk.Kh, a.kk.Kl, st);   // layers.py:112 / kernels.py:123
   if (rc) return rc;
-  if (d->kind == DCGP_LAYER_CONV) return tc_cond(prep, a.kk, n_rows * v.P, Mp, R, acc, mean_t, st);
+  if (d->kind == DCGP_LAYER_CONV) {
+    if (tc_forward_chained()) return tc_cond_chained(prep, a.kk, n_rows * v.P, Mp, R, variance, acc, mean_t, st);
+    return tc_cond(prep, a.kk, n_rows * v.P, Mp, R, acc, mean_t, st);
+  }
   patch_mean_planes_kernel<<<dim3(ceil_div(Mp, 128), n_rows), 128, 0, st>>>((const __half*)a.kk.Kh, (const __half*)a.kk.Kl, v.P, Mp,
                                                                           patch_weights, a.kk.kscal, Kzx);
   if ((rc = check_launch("patch_mean_planes"))) return rc;

@@ -34,19 +34,26 @@ int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double*
                      int R, cudaStream_t st);
 int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double* G, int ldg, int g_is_linv,
                       const double* Lpinv, int ldp, const double* q_sqrt, const double* beta, double* trace_out,
-                      const double* Kinv, int parts, cudaStream_t st);   // parts: 1 = forward operands, 2 = KL trace + backward operands
+                      const double* Kinv, int parts, int chained, const double* alpha, cudaStream_t st);
+// parts: 1 = forward operands, 2 = KL trace + backward operands.  chained: the W blocks 1..R hold C_r^T (C_r = Lm^-1 L_r, or
+// L_r when whitened) and the mean rows alpha^T (alpha = Lm^-1 q_mu, or q_mu) for tc_cond_chained, instead of W_r / beta^T.
 int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st);
 
 struct TcCondWork {
   TcPrep prep;    // only carved by tc_carve_cond (the conditional() API mirror owns its operands)
   void *Kh, *Kl;  // [Tpad, Mp] fp16 planes of the kernel-matrix rows
   float* kscal;   // device: [0] = K scale, [1] = 1 / K scale
+  void *Ah, *Al;  // [Tpad, Mp] fp16 planes of a = Lm^-1 k (chained conditional, ConvLayer only; null otherwise)
+  float* ascal;   // device: {scale, 1/scale} of the a planes
   size_t Tpad;
   size_t bytes;
 };
 void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf);
 int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStream_t st);
 int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st);
+// chained form (prep.chained): a = K Lm^-T with |a|^2 -> acc[:, 0] and the a planes, then G_r = a C_r (upper-triangular operand)
+int tc_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc, float* mean, cudaStream_t st);
+bool tc_forward_chained();   // DCGP_FWD_CHAINED != 0 (default on)
 
 // Generic batched NT GEMM on split-fp16 planes: C[b][i,j] = sum_k A[b*a_batch_rows + i, k] * B[b*b_batch_rows + j, k].
 // Planes are row-major [rows_total, k_pad] fp16 (k_pad % 64 == 0, m_pad % 128 == 0, n_pad % 64 == 0, zero padded).
