@@ -347,7 +347,7 @@ def kernel_roofline(model, cfg, B, S, device, flush):
                  / launch duration;   peak = MEASURED_PEAKS.json bf16 burst (the kernel is timed alone);
       executed_* = the tensor-pipe flops the launch really issues: 3 split products x the k-blocks not skipped as zero;
       traffic = dram__bytes_read + dram__bytes_write of this launch from the committed `ncu --set full` capture
-                (profiles/r1b_ncu_full_layer2.csv)."""
+                (profiles/r1c_ncu_full_layer2.csv; dense form: profiles/r1b_ncu_full_layer2.csv)."""
     import torch
     from deepcgp_b200 import _lib
     from deepcgp_b200.grad import LayerBackward
@@ -409,22 +409,22 @@ def kernel_roofline(model, cfg, B, S, device, flush):
     # (dK: + the 64-deep mean tile; dQ: 6 of 8 output tiles per r)
     dk = tensor_entry("dk_gemm_kernel<256,true> (dK GEMM + fused dd epilogue, conv layer 2 backward)", ms_dk,
                       2.0 * T * R * M * M, 3 * 2.0 * T * (R * M * M + 64 * M),
-                      {"traffic": 1879259120, "tensor_pipe_active_pct_ncu": 78.4,
+                      {"traffic": 1903177696, "tensor_pipe_active_pct_ncu": 77.6,
                        "epilogue_bytes": 2.0 * 4 * T * M + 4.0 * T * M})
     dq = tensor_entry("xf_gemm_kernel<256> (dQ GEMM, in-smem column rescale, conv layer 2 backward)", ms_dq,
                       1.0 * T * R * M * M, 3 * 2.0 * T * R * M * M * 0.75,
-                      {"traffic": 790946688, "tensor_pipe_active_pct_ncu": 60.7})
+                      {"traffic": 790520072, "tensor_pipe_active_pct_ncu": 60.5})
     return {"bound": "tensor", "kernel": "tc_kernel<MODE_A,256> + tc_kernel<MODE_COND,256> (chained conditional GEMM, conv layer 2 "
                                          "forward)" if chained else "tc_kernel<MODE_COND,256> (conditional GEMM, conv layer 2 forward)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-            "traffic": 877827921, "ms": ms, "algorithmic_gflop": alg / 1e9,
+            "traffic": 1590374000 if chained else 877827921, "ms": ms, "algorithmic_gflop": alg / 1e9,
             "executed_tensor_gflop": executed / 1e9, "executed_tflops": executed / (ms * 1e-3) / 1e12,
             "executed_frac": executed / (ms * 1e-3) / 1e12 / peak,
-            "peak_source": src, "tensor_pipe_active_pct_ncu": 96.9,
+            "peak_source": src, "tensor_pipe_active_pct_ncu": 93.2 if chained else 96.9,
             "kuf": {"kernel": "kuf_tc_kernel<256> (conv layer 2)", "bound": "hbm", "ms": ms_kuf,
                     "achieved": kuf_bytes / (ms_kuf * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                     "frac": kuf_bytes / (ms_kuf * 1e-3) / 1e9 / hbm, "algorithmic_bytes": kuf_bytes,
-                    "traffic": 500990456, "executed_tensor_gflop": kuf_flops / 1e9,
+                    "traffic": 498662144, "executed_tensor_gflop": kuf_flops / 1e9,
                     "tensor_floor_ms": kuf_flops / (peak * 1e12) * 1e3},
             "dk_gemm": dk, "dq_gemm": dq}
 
