@@ -92,10 +92,13 @@ static F64Work carve_f64(int M, int R, void* ws) {
 //   white    : G = Lm^-1,   W_r = L_r^T G,                                   beta = G^T q_mu
 struct GInfo { const double* G; int ldg; };
 
-static int factor_and_G(const F64Work& w, int white, const double* q_mu, int* info, GInfo* gi, cudaStream_t st) {
+static int factor_only(const F64Work& w, int* info, cudaStream_t st) {
+  DCGP_TRY(potrf_f64(w.Kuu, w.M, w.M, w.invD, info, st));
+  return trtri_f64(w.Kuu, w.M, w.M, w.invD, w.Linv, w.trws, st);
+}
+
+static int g_and_beta(const F64Work& w, int white, const double* q_mu, GInfo* gi, cudaStream_t st) {
   const int M = w.M, R = w.R, Mq = w.Mq;
-  DCGP_TRY(potrf_f64(w.Kuu, M, M, w.invD, info, st));
-  DCGP_TRY(trtri_f64(w.Kuu, M, M, w.invD, w.Linv, w.trws, st));
   gi->G = w.Linv;
   gi->ldg = Mq;
   if (!white) {
@@ -114,6 +117,11 @@ static int factor_and_G(const F64Work& w, int white, const double* q_mu, int* in
   g.B = q_mu; g.ldb = R;
   g.C = w.beta; g.ldc = R; g.alpha = 1.0; g.batch = 1;
   return gemm_f64(g, st);
+}
+
+static int factor_and_G(const F64Work& w, int white, const double* q_mu, int* info, GInfo* gi, cudaStream_t st) {
+  DCGP_TRY(factor_only(w, info, st));
+  return g_and_beta(w, white, q_mu, gi, st);
 }
 
 static int wr_f64(const F64Work& w, int white, const GInfo& gi, const double* q_sqrt, cudaStream_t st) {
@@ -354,6 +362,38 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
     Lp = Kp;
     Lpinv = w.Lpinv;
   }
+  const int chained = (algo == DCGP_ALGO_TC && d->kind == DCGP_LAYER_CONV && tc_forward_chained()) ? 1 : 0;
+  if (chained) {
+    // The chained forward needs only Lm^-1, C_r^T and alpha: Kuu^-1 and beta (backward operands) wait behind the event.
+    DCGP_TRY(factor_only(w, info, st));
+    const double* alpha = q_mu;          // whitened: mean = a^T q_mu
+    if (!d->white) {                     // alpha = Lm^-1 q_mu
+      GemmF64 g{};
+      g.m = M; g.n = R; g.k = M;
+      g.A = w.Linv; g.lda = w.Mq; g.lowerA = 1;
+      g.B = q_mu; g.ldb = R;
+      g.C = w.alpha; g.ldc = R; g.alpha = 1.0; g.batch = 1;
+      DCGP_TRY(gemm_f64(g, st));
+      alpha = w.alpha;
+    }
+    DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, nullptr, 0, d->white ? 1 : 0, nullptr, w.Mq, q_sqrt, w.beta, w.sc + 1,
+                               nullptr, 1, 1, alpha, st));
+    DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+    if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
+    DCGP_TRY(g_and_beta(w, d->white, q_mu, &gi, st));
+    if (d->white) {   // Q_0 = Kuu^-1 is needed by the backward operands even when G = Lm^-1
+      GemmF64 g{};
+      g.m = g.n = g.k = M;
+      g.A = w.Linv; g.lda = w.Mq; g.transA = 1; g.lowerA = 1;
+      g.B = w.Linv; g.ldb = w.Mq; g.lowerB = 1;
+      g.C = w.Kinv; g.ldc = M; g.alpha = 1.0; g.batch = 1;
+      DCGP_TRY(gemm_f64(g, st));
+    }
+    if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
+    DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
+                               w.beta, w.sc + 1, w.Kinv, 2, 1, alpha, st));
+    return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
+  }
   DCGP_TRY(factor_and_G(w, d->white, q_mu, info, &gi, st));
   if (algo == DCGP_ALGO_TC) {
     if (d->white) {   // Q_0 = Kuu^-1 is needed by the backward operands even when G = Lm^-1
@@ -366,24 +406,13 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
     }
     // forward operands first; the caller's event marks the point from which dcgp_layer_apply may run -- the KL (which
     // joins the prior chain) and the backward operands follow on the same stream, off the forward's critical path
-    const int chained = (d->kind == DCGP_LAYER_CONV && tc_forward_chained()) ? 1 : 0;
-    const double* alpha = q_mu;          // whitened: mean = a^T q_mu
-    if (chained && !d->white) {          // alpha = Lm^-1 q_mu
-      GemmF64 g{};
-      g.m = M; g.n = R; g.k = M;
-      g.A = w.Linv; g.lda = w.Mq; g.lowerA = 1;
-      g.B = q_mu; g.ldb = R;
-      g.C = w.alpha; g.ldc = R; g.alpha = 1.0; g.batch = 1;
-      DCGP_TRY(gemm_f64(g, st));
-      alpha = w.alpha;
-    }
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, 1, chained, alpha, st));
+                               w.beta, w.sc + 1, w.Kinv, 1, 0, nullptr, st));
     DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
     if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
     if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, 2, chained, alpha, st));
+                               w.beta, w.sc + 1, w.Kinv, 2, 0, nullptr, st));
     return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
   }
   if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
