@@ -65,6 +65,7 @@ SIGNATURES = {
     "dcgp_convkernel_kzx_workspace_bytes": (_sz, [_pd, _i]),
     "dcgp_convkernel_kzx": (_i, [_pd, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "dcgp_convkernel_kdiag": (_i, [_pd, _vp, _vp, _i, _vp, _vp]),
+    "dcgp_randn": (_i, [_vp, _i, _i, _i, C.c_longlong, C.c_longlong, C.c_ulonglong, C.c_ulonglong, _i, _vp]),
     "dcgp_reparameterize": (_i, [_vp, _vp, _vp, _sz, _d, _vp, _vp]),
     "dcgp_multiclass_varexp": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),
     "dcgp_multiclass_predict": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp]),

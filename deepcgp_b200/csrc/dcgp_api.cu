@@ -616,6 +616,15 @@ int dcgp_convkernel_kdiag(const dcgp_layer_desc* d, const double* patch_weights,
   return launch_kdiag(X, v, N, patch_weights, (float)d->variance, inv_ls * inv_ls, out, (cudaStream_t)stream);
 }
 
+int dcgp_randn(float* z, int S, int n_local, int D, long long n_global, long long n0, unsigned long long seed,
+               unsigned long long step, int layer, void* stream) {
+  if (!z || S < 1 || n_local < 0 || D < 1 || n_global < n_local || n0 < 0 || n0 + n_local > n_global) {
+    set_error("randn: bad argument");
+    return DCGP_ERR_ARG;
+  }
+  return launch_randn(z, S, n_local, D, n_global, n0, seed, step, layer, (cudaStream_t)stream);
+}
+
 int dcgp_reparameterize(const float* mean, const float* var, const float* z, size_t n, double jitter, float* out,
                         void* stream) {
   if (!mean || !var || !z || !out) { set_error("reparameterize: null argument"); return DCGP_ERR_ARG; }

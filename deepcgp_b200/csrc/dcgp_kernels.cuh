@@ -38,6 +38,8 @@ int launch_cond_simt(const float* Kt, int T, int ld, int Mp, const float* W, con
 int launch_finalize(const float* acc, const float* mean_t, int T, int R, float knn_const, const float* knn_vec,
                     int n_rep, const float* z, float jitter, float* mean, float* var, float* sample, cudaStream_t st);
 int launch_finalize_ref_layout(const float* acc, const float* Knn, int P, int N, int R, float* fvar, cudaStream_t st);
+int launch_randn(float* z, int S, int n_local, int D, long long n_global, long long n0, unsigned long long seed,
+                 unsigned long long step, int layer, cudaStream_t st);
 int launch_reparam(const float* mean, const float* var, const float* z, size_t n, float jitter, float* out, cudaStream_t st);
 int launch_patch_mean(const float* Kt, int n_rows, int P, int ld, int M, const double* w, int trans, int ldo, float* out,
                       cudaStream_t st);

@@ -406,6 +406,47 @@ int launch_kdiag(const float* X, const View& v, int n_rows, const double* w, flo
   return check_launch("kdiag");
 }
 
+// ------------------------------------------------------------------------------------------ a8: N(0,1) draws
+// tf.random_normal of DS/layers.py:104, as a COUNTER-BASED generator (Philox-4x32-10 + Box-Muller) keyed by
+// (seed, step, layer) and indexed by (sample, GLOBAL image index, output): the draw of an image does not depend on which
+// rank holds it or on how many ranks there are, so 1/2/4/8-GPU runs of the same step see identical noise.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ z, int S, int n_local, int D, long long n_global,
+                                                    long long n0, unsigned long long seed, unsigned long long step, int layer) {
+  const long long total = (long long)S * n_local * D;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    const int d = (int)(e % D);
+    const long long q = e / D;
+    const int n = (int)(q % n_local), s = (int)(q / n_local);
+    const unsigned long long idx = ((unsigned long long)s * (unsigned long long)n_global + (unsigned long long)(n0 + n)) * D + d;
+    uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)layer << 16)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
+    const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    z[e] = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+  }
+}
+
+int launch_randn(float* z, int S, int n_local, int D, long long n_global, long long n0, unsigned long long seed,
+                 unsigned long long step, int layer, cudaStream_t st) {
+  const long long total = (long long)S * n_local * D;
+  if (total <= 0) return DCGP_OK;
+  long long blocks = (total + 1023) / 1024;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  randn_kernel<<<(unsigned)blocks, 256, 0, st>>>(z, S, n_local, D, n_global, n0, seed, step, layer);
+  return check_launch("randn");
+}
+
 // ------------------------------------------------------------------------------------------ a9: likelihood
 __constant__ double c_gh_x[20];
 __constant__ double c_gh_w[20];  // already divided by sqrt(pi)

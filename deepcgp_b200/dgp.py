@@ -29,7 +29,7 @@ class Minibatch(object):
 
 class DGP_Base(object):
     def __init__(self, X, Y, likelihood, layers, minibatch_size=None, num_samples=1, num_data=None, device="cuda",
-                 **kwargs):
+                 seed=0, **kwargs):
         self.num_samples = int(num_samples)
         self.num_data = num_data or X.shape[0]                              # DS/dgp.py:49
         self.device = torch.device(device)
@@ -42,6 +42,26 @@ class DGP_Base(object):
         self._sum = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._elbo = torch.zeros(1, dtype=torch.float64, device=self.device)
         self._side = None
+        self.seed = int(seed)
+        self._z_step = 0
+
+    def draw_zs(self, n_local, n_global=None, n0=0, step=None):
+        """The N(0,1) draws of one step (tf.random_normal at DS/layers.py:104), one [S, n_local, D_l] tensor per layer, from
+        the counter-based generator dcgp_randn: the draw for (layer, sample, GLOBAL image n0 + n, output) depends only on
+        (seed, step) -- not on the rank that holds the image, so image-sharded runs on any number of GPUs see the same
+        noise.  `step` defaults to an internal counter that advances by one per call."""
+        if step is None:
+            self._z_step += 1
+            step = self._z_step
+        S = self.num_samples
+        n_global = int(n_global or n_local)
+        zs = []
+        for li, layer in enumerate(self.layers):
+            z = torch.empty((S, int(n_local), layer.num_outputs), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.dcgp_randn(_lib.ptr(z), S, int(n_local), layer.num_outputs, n_global, int(n0), self.seed,
+                                           int(step), li, _lib.stream()))
+            zs.append(z)
+        return zs
 
     # ------------------------------------------------------------------ DS/dgp.py:61-76
     def propagate(self, X, full_cov=False, S=1, zs=None):

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .dist import allreduce_sum_, world
+from .dist import allreduce_sum_, shard_range, world
 from .kernels import JITTER
 from .layers import ConvLayer
 
@@ -256,8 +256,11 @@ class ElboGradient(object):
         model = self.model
         X = _lib.f32(X, model.device)
         N, S = X.shape[0], model.num_samples
-        if zs is None:
-            zs = [torch.randn((S, N, l.num_outputs), dtype=torch.float32, device=model.device) for l in model.layers]
+        if zs is None:      # rank-count-invariant draws: indexed by the GLOBAL position of this rank's images
+            rank, wsize = world()
+            n_g = int(n_global or N)
+            n0 = shard_range(n_g, rank, wsize)[0] if n_g != N else 0
+            zs = model.draw_zs(N, n_g, n0)
         zs = [_lib.f32(z, model.device) for z in zs]
         elbo = model._build_likelihood(X, Y, zs=zs, n_global=n_global, keep=True)
         Fs, Fmeans, Fvars = model._fwd

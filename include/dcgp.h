@@ -183,6 +183,12 @@ int dcgp_convkernel_kzx(const dcgp_layer_desc* d, const double* Z, const double*
 int dcgp_convkernel_kdiag(const dcgp_layer_desc* d, const double* patch_weights, const float* X, int N,
                           float* out, void* stream);
 
+/* tf.random_normal of DS/layers.py:104 as a counter-based generator (Philox-4x32-10 + Box-Muller): z[S, n_local, D] float32,
+ * the draw for (sample s, GLOBAL image n0 + n, output d) depends only on (seed, step, layer, s, n0 + n, d, n_global), not
+ * on the rank that holds the image -- image-sharded runs on 1/2/4/8 GPUs see identical noise. */
+int dcgp_randn(float* z, int S, int n_local, int D, long long n_global, long long n0, unsigned long long seed,
+               unsigned long long step, int layer, void* stream);
+
 /* DS/utils.py:40-41 reparameterize (diag): out = mean + z*sqrt(var + jitter). */
 int dcgp_reparameterize(const float* mean, const float* var, const float* z, size_t n, double jitter,
                         float* out, void* stream);

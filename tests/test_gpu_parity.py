@@ -396,3 +396,52 @@ def test_s_broadcast_equals_tiling():
     torch.testing.assert_close(m1, m2, rtol=0, atol=0)
     torch.testing.assert_close(v1, v2, rtol=0, atol=0)
     torch.testing.assert_close(s1, s2, rtol=0, atol=0)
+
+
+# ----------------------------------------------------------------------------------------------- 8e: rank-invariant noise
+def test_counter_based_normals_are_shard_invariant_and_standard():
+    """dcgp_randn (the stand-in for tf.random_normal, DS/layers.py:104): the draw of an image depends on its GLOBAL index
+    only, so a batch sharded over ranks reproduces the unsharded draws bit for bit; moments of N(0,1)."""
+    g = load_golden("dgp2_elbo")
+    layers = layers_from_golden(g)
+    model = build_model(layers, g["X"].astype(np.float32), g["Y"], 3, 100.0, "tc")
+    full = model.draw_zs(8, 8, 0, step=5)
+    a = model.draw_zs(3, 8, 0, step=5)
+    b = model.draw_zs(5, 8, 3, step=5)
+    for zf, za, zb in zip(full, a, b):
+        assert torch.equal(zf, torch.cat([za, zb], dim=1))
+    other = model.draw_zs(8, 8, 0, step=6)
+    assert not torch.equal(full[0], other[0])
+    from deepcgp_b200 import _lib
+    z = torch.empty((4, 1000, 500), dtype=torch.float32, device=dev())
+    _lib.check(_lib.lib.dcgp_randn(_lib.ptr(z), 4, 1000, 500, 1000, 0, 12345, 1, 0, _lib.stream()))
+    zz = z.double()
+    assert abs(float(zz.mean())) < 3e-3
+    assert abs(float(zz.var()) - 1.0) < 5e-3
+    assert abs(float((zz ** 4).mean()) - 3.0) < 5e-2
+    assert float(zz.abs().max()) < 7.0 and bool(torch.isfinite(z).all())
+    # successive samples / images / outputs are uncorrelated
+    assert abs(float((zz[:, :, :-1] * zz[:, :, 1:]).mean())) < 3e-3
+    assert abs(float((zz[:, :-1] * zz[:, 1:]).mean())) < 3e-3
+    assert abs(float((zz[:-1] * zz[1:]).mean())) < 3e-3
+
+
+def test_elbo_data_term_is_additive_over_image_shards():
+    """ELBO = scale * sum_n l_n - sum KL, so the data terms of two image shards (with the draws of their GLOBAL
+    image indices) add up to the unsharded one."""
+    g = load_golden("dgp3_elbo")
+    layers = layers_from_golden(g)
+    S = int(g["S"])
+    X32 = g["X"].astype(np.float32)
+    N = X32.shape[0]
+    Y = np.asarray(g["Y"]).reshape(-1)
+    model = build_model(layers, X32, g["Y"], S, float(g["num_data"]), "tc")
+    zs = model.draw_zs(N, N, 0, step=1)
+    full = model.compute_log_likelihood(X32, Y, zs=zs)
+    kl = float(model._kls.sum().item())
+    parts = 0.0
+    for lo, hi in ((0, 1), (1, N)):
+        zsh = model.draw_zs(hi - lo, N, lo, step=1)
+        e = float(model._build_likelihood(X32[lo:hi], Y[lo:hi], zs=zsh, n_global=N).item())
+        parts += e + kl
+    assert abs((full + kl) - parts) <= 1e-6 * abs(full + kl), (full, parts, kl)
