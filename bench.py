@@ -234,9 +234,10 @@ def run_ours(args, cfg):
     hostY = [torch.from_numpy(rng.randint(0, 10, size=(B,)).astype(np.int32)).pin_memory() for _ in range(n_batches)]
     devX = [x.to(device) for x in hostX]
     devY = [y.to(device) for y in hostY]
-    gen = torch.Generator(device=device).manual_seed(777 + rank)
-    dims = [l.num_outputs for l in model.layers]
-    zs = [torch.randn((S, B, d), device=device, generator=gen) for d in dims]   # fixed N(0,1) draws, resident in HBM
+    # The N(0,1) draws of DS/layers.py:104 are part of the step: drawn inside the timed region, every step, by the
+    # counter-based generator (indexed by the global image position, so every rank count sees the same noise).
+    def draw():
+        return model.draw_zs(B, n_global, rank * B)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # > 126 MB L2
     elbo_host = torch.empty(1, dtype=torch.float64).pin_memory()
 
@@ -251,12 +252,12 @@ def run_ours(args, cfg):
         """One optimisation step: forward ELBO, backward, (all-reduce of the gradient), Adam update of every trainable.
         Default = grad.TrainStep (same arithmetic as ElboGradient + Adam.step, per-layer tails overlapped)."""
         if args.forward_only:
-            return model._build_likelihood(x, y, zs=zs, n_global=n_global)
+            return model._build_likelihood(x, y, zs=draw(), n_global=n_global)
         if args.sequential:
-            e, grads = eg(x, y, zs=zs, n_global=n_global)
+            e, grads = eg(x, y, zs=draw(), n_global=n_global)
             opt.step(grads)
             return e
-        return train_step(x, y, zs=zs, n_global=n_global)
+        return train_step(x, y, zs=draw(), n_global=n_global)
 
     def step_resident(i):
         return elbo_step(devX[i % n_batches], devY[i % n_batches])
