@@ -131,6 +131,17 @@ class LayerBackward(object):
         ob, ld = self._boff
         return layer._prep[ob:ob + R * ld * ld * 4].view(torch.float32).view(R, ld, ld)[:, :M, :M]
 
+    # GEMM shapes cuBLAS handles well: a matrix times every member of a stack as ONE [M,M] x [M,R*M] product, and
+    # sum_r A_r B_r^T as a batched product + a reduction (the [M,R*M] x [R*M,M] form gets 32x32 tiles and 4 TFLOP/s)
+    @staticmethod
+    def _left(Am, B3):
+        R_, M_, N_ = B3.shape
+        return (Am @ B3.permute(1, 0, 2).reshape(M_, R_ * N_)).reshape(M_, R_, N_).permute(1, 0, 2)
+
+    @staticmethod
+    def _bsum(A3, B3):
+        return torch.bmm(A3, B3.transpose(1, 2)).sum(0)
+
     @torch.no_grad()
     def m_only_static(self, kl_weight=1.0, hyp=None):
         """The part of the (non-whitened) chain rule that depends only on the parameters and on this step's
@@ -151,8 +162,7 @@ class LayerBackward(object):
         conv = isinstance(layer, ConvLayer)
         bt = self.BATCHED_DTYPE
 
-        def stack(T3):                                                   # [R,M,M] -> [M, R*M]: sum_r A_r B_r^T as ONE GEMM
-            return T3.permute(1, 0, 2).reshape(M, R * M)
+        bsum, left = self._bsum, self._left
 
         # The R-batched M^3 products run in BATCHED_DTYPE (float32 by default: their inputs -- dQ from the split-fp16
         # GEMMs, B_r from the forward -- carry 22-24 bits anyway, and cuBLAS float64 batched GEMMs reach only ~5 TFLOP/s
@@ -167,12 +177,12 @@ class LayerBackward(object):
             Zp = layer.Z_prior.to(torch.float64)
             Kpn, Dp = self._rbf_parts(Zp, var, ls)
             Kpinv = Lpinv.T @ Lpinv
-            Cb = Kpinv.to(bt) @ Lqb
+            Cb = left(Kpinv.to(bt), Lqb)
             a = Kpinv @ q_mu
         else:
             Kpinv, Cb = Kinv, Bb
             a = Kinv @ q_mu
-        dKL_dKp = 0.5 * (-(a @ a.T) - (stack(Cb) @ stack(Cb).T).to(torch.float64) + R * Kpinv)
+        dKL_dKp = 0.5 * (-(a @ a.T) - bsum(Cb, Cb).to(torch.float64) + R * Kpinv)
         g_qmu_kl = -kl_weight * a
         gLq_kl = -kl_weight * (Cb.to(torch.float64) - torch.diag_embed(1.0 / torch.diagonal(Lq, dim1=1, dim2=2)))
         if conv:
@@ -181,7 +191,7 @@ class LayerBackward(object):
         else:
             GU_kl = -kl_weight * dKL_dKp
             gvar_p = gls_p = 0.0
-        return dict(Z=Z, var=var, ls=ls, q_mu=q_mu, Kn=Kn, D=D, Kinv=Kinv, Kinvb=Kinvb, Bb=Bb, LqbT=stack(Lqb).T.contiguous(),
+        return dict(Z=Z, var=var, ls=ls, q_mu=q_mu, Kn=Kn, D=D, Kinv=Kinv, Kinvb=Kinvb, Bb=Bb, Lqb=Lqb,
                     g_qmu_kl=g_qmu_kl, gLq_kl=gLq_kl, GU_kl=GU_kl, gvar_p=gvar_p, gls_p=gls_p)
 
     @torch.no_grad()
@@ -198,8 +208,8 @@ class LayerBackward(object):
         gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
         Kinv = st["Kinv"]
         Ub = (gQ[1:] + gQ[1:].transpose(1, 2)).to(bt) @ st["Bb"]         # d/dB_r
-        gLq = (st["Kinvb"] @ Ub).to(torch.float64) + st["gLq_kl"]        # d/dL_r (through B_r) + KL
-        GK = gQ[0] + (Ub.permute(1, 0, 2).reshape(M, R * M) @ st["LqbT"]).to(torch.float64) + gbeta @ st["q_mu"].T   # d/dKinv
+        gLq = self._left(st["Kinvb"], Ub).to(torch.float64) + st["gLq_kl"]   # d/dL_r (through B_r) + KL
+        GK = gQ[0] + self._bsum(Ub, st["Lqb"]).to(torch.float64) + gbeta @ st["q_mu"].T   # d/dKinv
         g_qmu = Kinv @ gbeta + st["g_qmu_kl"]
         GU = -(Kinv @ GK @ Kinv)                                         # d/dKuu
         if st["GU_kl"] is not None:
