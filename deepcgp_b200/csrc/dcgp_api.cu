@@ -563,6 +563,21 @@ int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep_buf, const vo
                                     gw, ws, ws_bytes, 3, stream);
 }
 
+size_t dcgp_bgemm_workspace_bytes(int batch, int m, int n, int k) {
+  if (batch < 1 || m < 1 || n < 1 || k < 1) return 0;
+  return tc_bgemm_workspace_bytes(batch, m, n, k);
+}
+
+int dcgp_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride,
+                  long long b_bstride, void* ws, size_t ws_bytes, void* stream) {
+  if (!A || !B || !C || batch < 1 || m < 1 || n < 1 || k < 1 || a_bstride < 0 || b_bstride < 0 || (n % 4) != 0) {
+    set_error("bgemm_nt: bad argument (n must be a multiple of 4)");
+    return DCGP_ERR_ARG;
+  }
+  if (!ws || ws_bytes < dcgp_bgemm_workspace_bytes(batch, m, n, k)) { set_error("bgemm_nt: workspace too small"); return DCGP_ERR_WORKSPACE; }
+  return tc_bgemm_nt(A, B, C, batch, m, n, k, a_bstride, b_bstride, ws, (cudaStream_t)stream);
+}
+
 int dcgp_multiclass_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,
                                 double coef, float* gmu, float* gvar, void* stream) {
   if (!Fmu || !Fvar || !Y || !gmu || !gvar || S < 1 || N < 1) { set_error("varexp_grad: bad argument"); return DCGP_ERR_ARG; }

@@ -773,6 +773,25 @@ static int pack_planes_f64(const double* src, int ld, long long bstride, int row
   return check_launch("pack_planes_f64");
 }
 
+// fp32 -> split-fp16 planes: dst[b*rows_pad + i, j] = s * src[b*bstride + i*ld + j], zero padding elsewhere
+__global__ void __launch_bounds__(256) pack_planes_f32_kernel(const float* __restrict__ src, int ld, long long bstride, int rows,
+                                                              int cols, int batch, int rows_pad, int cols_pad,
+                                                              const float* __restrict__ scal2, __half* __restrict__ Ph,
+                                                              __half* __restrict__ Pl) {
+  const float s = scal2[0];
+  const long long total = (long long)batch * rows_pad * cols_pad;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
+    const int j = (int)(e % cols_pad);
+    const long long q = e / cols_pad;
+    const int i = (int)(q % rows_pad), b = (int)(q / rows_pad);
+    const float v = (i < rows && j < cols) ? s * src[b * bstride + (long long)i * ld + j] : 0.f;
+    __half hi, lo;
+    split_f16(v, hi, lo);
+    Ph[e] = hi;
+    Pl[e] = lo;
+  }
+}
+
 // W planes: rows [0, (R+1)*Mp) = blocks (block 0 = Linv, block r = Wr[r-1]), then the mean rows (beta^T), then zero padding.
 // Wr comes either as float64 [R, M, M] (Wr64) or as float32 [R*Mp, Mp] (Wr32, the tensor-core product).
 __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, const double* __restrict__ Wr64,
@@ -871,6 +890,55 @@ struct Carve2 {
     return r;
   }
 };
+
+// Generic batched C[b] = A[b] B[b]^T for float32 operands on the split-fp16 tensor-core GEMM (the R-batched M^3 products of
+// the host's M-only chain rule): A [batch or 1, m, k], B [batch or 1, n, k] row-major, C [batch, m, n]; a batch stride of 0
+// broadcasts the operand.  ~22-bit products, fp32 accumulation.
+struct BgemmWork {
+  void *Ah, *Al, *Bh, *Bl;
+  float *scal, *mx;
+  int m_pad, n_pad, k_pad;
+  size_t bytes;
+};
+static BgemmWork carve_bgemm(int batch, int m, int n, int k, void* buf) {
+  BgemmWork w;
+  w.m_pad = (int)align_up(m, kBM); w.n_pad = (int)align_up(n, 64); w.k_pad = (int)align_up(k, kBK);
+  Carve2 c(buf);
+  w.Ah = c.take((size_t)batch * w.m_pad * w.k_pad * 2 + 256 * (size_t)w.k_pad * 2);   // + slack: a 128/256-row TMA box may overrun
+  w.Al = c.take((size_t)batch * w.m_pad * w.k_pad * 2 + 256 * (size_t)w.k_pad * 2);
+  w.Bh = c.take((size_t)batch * w.n_pad * w.k_pad * 2 + 256 * (size_t)w.k_pad * 2);
+  w.Bl = c.take((size_t)batch * w.n_pad * w.k_pad * 2 + 256 * (size_t)w.k_pad * 2);
+  w.scal = (float*)c.take(8 * 4);
+  w.mx = (float*)c.take(4 * 4);
+  w.bytes = align_up(c.off, 1024);
+  return w;
+}
+size_t tc_bgemm_workspace_bytes(int batch, int m, int n, int k) { return carve_bgemm(batch, m, n, k, nullptr).bytes + 1024; }
+
+int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride, long long b_bstride,
+                void* ws, cudaStream_t st) {
+  BgemmWork w = carve_bgemm(batch, m, n, k, (void*)align_up((size_t)ws, 1024));
+  const int ab = a_bstride ? batch : 1, bb = b_bstride ? batch : 1;
+  int rc;
+  cudaMemsetAsync(w.mx, 0, 4 * sizeof(float), st);
+  if ((rc = maxabs_f32(A, (long long)ab * m * k, w.mx + 0, st))) return rc;
+  if ((rc = maxabs_f32(B, (long long)bb * n * k, w.mx + 1, st))) return rc;
+  scales_from_max_kernel<<<1, 32, 0, st>>>(w.mx, 0, 2, w.scal);
+  pack_planes_f32_kernel<<<grid_for((long long)ab * w.m_pad * w.k_pad, 2048), 256, 0, st>>>(A, k, (long long)m * k, m, k, ab, w.m_pad, w.k_pad,
+                                                                                          w.scal + 0, (__half*)w.Ah, (__half*)w.Al);
+  pack_planes_f32_kernel<<<grid_for((long long)bb * w.n_pad * w.k_pad, 2048), 256, 0, st>>>(B, k, (long long)n * k, n, k, bb, w.n_pad, w.k_pad,
+                                                                                          w.scal + 2, (__half*)w.Bh, (__half*)w.Bl);
+  if ((rc = check_launch("bgemm_pack", 3))) return rc;
+  TcGemm g;
+  memset(&g, 0, sizeof(g));
+  g.Ah = w.Ah; g.Al = w.Al; g.a_rows_total = (long long)ab * w.m_pad; g.a_batch_rows = a_bstride ? w.m_pad : 0;
+  g.Bh = w.Bh; g.Bl = w.Bl; g.b_rows_total = (long long)bb * w.n_pad; g.b_batch_rows = b_bstride ? w.n_pad : 0;
+  g.batch = batch; g.m = m; g.n = n; g.m_pad = w.m_pad; g.n_pad = w.n_pad; g.k_pad = w.k_pad;
+  g.a_scal = w.scal + 0; g.b_scal = w.scal + 2;
+  g.C = C; g.c_batch_stride = (long long)m * n; g.ldc = n;
+  return tc_gemm(g, st);
+}
+
 
 void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   memset(&t, 0, sizeof(t));

@@ -69,6 +69,9 @@ struct TcGemm {
   int bf16;                                      // planes are bf16 hi/lo (unscaled values allowed) instead of fp16
   int splits; long long c_split_stride;          // split-K: partial C per split (caller reduces); splits <= 1 = off
 };
+size_t tc_bgemm_workspace_bytes(int batch, int m, int n, int k);
+int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride, long long b_bstride,
+                void* ws, cudaStream_t st);
 int tc_gemm_splits(const TcGemm& g);             // number of splits tc_gemm will really use
 int tc_gemm(const TcGemm& g, cudaStream_t st);
 

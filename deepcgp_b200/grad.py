@@ -35,6 +35,7 @@ class LayerBackward(object):
     """Per-layer buffers + the M-only chain rule."""
 
     BATCHED_DTYPE = torch.float32     # dtype of the R-batched M^3 products of the chain rule (torch.float64 = all-double)
+    TC_BATCHED = True                 # float32 batched products on the library's split-fp16 tcgen05 GEMM (dcgp_bgemm_nt)
 
     def __init__(self, layer):
         self.layer = layer
@@ -131,15 +132,43 @@ class LayerBackward(object):
         ob, ld = self._boff
         return layer._prep[ob:ob + R * ld * ld * 4].view(torch.float32).view(R, ld, ld)[:, :M, :M]
 
-    # GEMM shapes cuBLAS handles well: a matrix times every member of a stack as ONE [M,M] x [M,R*M] product, and
-    # sum_r A_r B_r^T as a batched product + a reduction (the [M,R*M] x [R*M,M] form gets 32x32 tiles and 4 TFLOP/s)
-    @staticmethod
-    def _left(Am, B3):
-        R_, M_, N_ = B3.shape
+    # The R-batched M^3 products of the chain rule: on the library's own tcgen05 GEMM (default), else through cuBLAS in shapes
+    # it handles well (the [M,R*M] x [R*M,M] form of sum_r A_r B_r^T gets 32x32 tiles and 4 TFLOP/s: bmm + reduction instead)
+    def _use_tc(self):
+        return (self.TC_BATCHED and self.BATCHED_DTYPE == torch.float32 and self.layer._algo() == _lib.ALGO_TC
+                and self.M % 4 == 0)        # (the GEMM's vectorised stores need a row length that is a multiple of 4)
+
+    def _gemm_nt(self, A, B):
+        """C[r] = A[r] @ B[r]^T (float32; a 2-D operand is shared by every r) on the tensor cores via dcgp_bgemm_nt."""
+        A, B = A.contiguous(), B.contiguous()
+        batch = B.shape[0] if B.dim() == 3 else A.shape[0]
+        m, k = A.shape[-2], A.shape[-1]
+        n = B.shape[-2]
+        Cm = torch.empty((batch, m, n), dtype=torch.float32, device=A.device)
+        nbytes = _lib.lib.dcgp_bgemm_workspace_bytes(batch, m, n, k)
+        ws = self.ws.get("bgemm", nbytes, A.device)
+        _lib.check(_lib.lib.dcgp_bgemm_nt(_lib.ptr(A), _lib.ptr(B), _lib.ptr(Cm), batch, m, n, k,
+                                          m * k if A.dim() == 3 else 0, n * k if B.dim() == 3 else 0,
+                                          _lib.ptr(ws), ws.numel(), _lib.stream()))
+        return Cm
+
+    def _left(self, Am, B3):
+        """Am @ B_r for every r."""
+        if self._use_tc():
+            return self._gemm_nt(Am, B3.transpose(1, 2))
+        R_, M_, N_ = B3.shape          # one [M,M] x [M,R*M] product (cuBLAS gets 32x32 tiles for the broadcast-batched form)
         return (Am @ B3.permute(1, 0, 2).reshape(M_, R_ * N_)).reshape(M_, R_, N_).permute(1, 0, 2)
 
-    @staticmethod
-    def _bsum(A3, B3):
+    def _bmm(self, A3, B3):
+        """A_r @ B_r for every r."""
+        if self._use_tc():
+            return self._gemm_nt(A3, B3.transpose(1, 2))
+        return torch.bmm(A3, B3)
+
+    def _bsum(self, A3, B3):
+        """sum_r A_r @ B_r^T"""
+        if self._use_tc():
+            return self._gemm_nt(A3, B3).sum(0)
         return torch.bmm(A3, B3.transpose(1, 2)).sum(0)
 
     @torch.no_grad()
@@ -172,7 +201,7 @@ class LayerBackward(object):
         if layer._algo() == _lib.ALGO_TC:
             Bb = self._forward_B().to(bt)                                # [R,M,M] = Kinv @ Lq, already formed this step
         else:
-            Bb = Kinvb @ Lqb
+            Bb = self._left(Kinvb, Lqb).contiguous()
         if conv:    # prior = Kuu at the initial Z (a constant) with the live hyper-parameters (layers.py:149-150)
             Zp = layer.Z_prior.to(torch.float64)
             Kpn, Dp = self._rbf_parts(Zp, var, ls)
@@ -207,7 +236,7 @@ class LayerBackward(object):
         gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
         gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
         Kinv = st["Kinv"]
-        Ub = (gQ[1:] + gQ[1:].transpose(1, 2)).to(bt) @ st["Bb"]         # d/dB_r
+        Ub = self._bmm((gQ[1:] + gQ[1:].transpose(1, 2)).to(bt), st["Bb"])   # d/dB_r
         gLq = self._left(st["Kinvb"], Ub).to(torch.float64) + st["gLq_kl"]   # d/dL_r (through B_r) + KL
         GK = gQ[0] + self._bsum(Ub, st["Lqb"]).to(torch.float64) + gbeta @ st["q_mu"].T   # d/dKinv
         g_qmu = Kinv @ gbeta + st["g_qmu_kl"]

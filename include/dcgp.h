@@ -166,6 +166,13 @@ int dcgp_layer_backward_phases(const dcgp_layer_desc* d, const void* prep, const
                                const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
                                const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw,
                                void* ws, size_t ws_bytes, int phases, void* stream);
+/* Batched C[b] = A[b] B[b]^T, float32 in / out, on the split-fp16 tcgen05 GEMM (22-bit products, fp32 accumulation): the
+ * R-batched M^3 products of the M-only chain rule (what tf.gradients emits as batched MatMul ops).  A [batch or 1, m, k],
+ * B [batch or 1, n, k], C [batch, m, n], all row-major contiguous; a batch stride (in elements) of 0 broadcasts the operand;
+ * n % 4 == 0. */
+size_t dcgp_bgemm_workspace_bytes(int batch, int m, int n, int k);
+int dcgp_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride,
+                  long long b_bstride, void* ws, size_t ws_bytes, void* stream);
 /* gradient of coef * sum(varexp) w.r.t. Fmu, Fvar ([S*N, K] float32) */
 int dcgp_multiclass_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K,
                                 double epsilon, double coef, float* gmu, float* gvar, void* stream);
