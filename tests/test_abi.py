@@ -83,3 +83,22 @@ def test_minibatch_is_seeded_and_covers_the_data():
     ib = [b.next_indices() for _ in range(6)]
     assert all((x == y).all() for x, y in zip(ia, ib))
     assert sorted(np.concatenate(ia[:3]).tolist()) == sorted(set(np.concatenate(ia[:3]).tolist()))
+
+
+def test_new_entry_points_validate_arguments_on_the_host():
+    """Entry points added for the backward split, the prediction path, the counter-based noise and the batched GEMM reject
+    bad arguments before touching the device."""
+    from deepcgp_b200 import _lib
+    lib = _lib.lib
+    d = _lib.LayerDesc(_lib.LAYER_CONV, 8, 8, 1, 3, 1, 4, 2, 0, 1.0, 1.0, 1e-3)
+    # phases outside 1..3 / null buffers
+    assert lib.dcgp_layer_backward_phases(d, None, None, None, None, None, 1, 1, None, None, None, None, None, None, None,
+                                          None, 0, 3, None) == _lib.DCGP_ERR_ARG
+    assert lib.dcgp_multiclass_predict(None, None, None, 1, 1, 10, 1e-3, None, None, None, None) == _lib.DCGP_ERR_ARG
+    assert lib.dcgp_randn(None, 1, 1, 1, 1, 0, 0, 0, 0, None) == _lib.DCGP_ERR_ARG
+    assert lib.dcgp_bgemm_nt(None, None, None, 1, 4, 4, 4, 0, 0, None, 0, None) == _lib.DCGP_ERR_ARG
+    assert lib.dcgp_bgemm_workspace_bytes(10, 512, 512, 512) > 4 * 10 * 512 * 512 * 2
+    assert lib.dcgp_bgemm_workspace_bytes(0, 1, 1, 1) == 0
+    off, ld = C.c_size_t(), C.c_int()
+    assert lib.dcgp_prepare_layout(d, C.byref(off), C.byref(ld)) == _lib.DCGP_OK
+    assert ld.value == 64 and 0 < off.value < lib.dcgp_prepare_bytes(d)
