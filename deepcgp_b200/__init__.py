@@ -21,3 +21,4 @@ from .layers import ConvLayer, Layer, MultiOutputConvKernel, SVGP_Layer, Zero  #
 from .likelihoods import BroadcastingLikelihood, MultiClass  # noqa: E402,F401
 from .dgp import DGP_Base  # noqa: E402,F401
 from .grad import Adam, ElboGradient, TrainStep  # noqa: E402,F401
+from .models import ModelBuilder, save_model_parameters  # noqa: E402,F401

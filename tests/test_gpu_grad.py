@@ -158,3 +158,42 @@ def test_pipelined_train_step_equals_sequential_steps(name):
     for l1, l2 in zip(m1.layers, m2.layers):
         assert abs(l1._base_kernel.variance - l2._base_kernel.variance) <= 1e-9 * abs(l1._base_kernel.variance)
         assert abs(l1._base_kernel.lengthscales - l2._base_kernel.lengthscales) <= 1e-9 * abs(l1._base_kernel.lengthscales)
+
+
+def test_model_builder_checkpoint_roundtrip(tmp_path):
+    """ModelBuilder (models.py:35-198: k-means patch init, identity_conv shape propagation, q_sqrt x 1e-5),
+    a few optimisation steps, experiment.py:56-64 parameter dump, and a rebuild from it (models.py:200-233)."""
+    import deepcgp_b200 as D
+    from deepcgp_b200 import models as Mo
+    rng = np.random.RandomState(0)
+    X = rng.standard_normal((40, 12, 12, 1))
+    Y = rng.randint(0, 10, size=(40, 1))
+    flags = Mo.default_parser().parse_args(["-M", "8,8", "--feature-maps", "3", "--filter-sizes", "5,3", "--strides", "2,1",
+                                            "--batch-size", "8", "--num-samples", "2"])
+    model = Mo.ModelBuilder(flags, X, Y, device=dev()).build()
+    assert [type(l).__name__ for l in model.layers] == ["ConvLayer", "SVGP_Layer"]
+    l0, l1 = model.layers
+    assert l0.feature.Z.shape == (8, 25) and l0.num_outputs == 16 * 3 and l1.feature.Z.shape == (8, 9 * 3)
+    assert float(l0._base_kernel.variance) == 5.0 and float(l0._base_kernel.lengthscales) == 5.0        # models.py:115-116
+    Ku = D.MultiOutputConvKernel(l0.base_kernel, 144, 16).Kuu(l0.feature.Z)
+    np.testing.assert_allclose(npy(l0.q_sqrt[0]), 1e-5 * np.linalg.cholesky(npy(Ku)), rtol=1e-6, atol=1e-12)
+    step = D.TrainStep(model, lr=0.01)
+    Xb = X[:8].reshape(8, -1).astype(np.float32)
+    for _ in range(3):
+        step(Xb, Y[:8])
+    step.finish()
+    torch.cuda.synchronize()
+    path = str(tmp_path / "model.npy")
+    Mo.save_model_parameters(model, path, global_step=3)
+    saved = np.load(path, allow_pickle=True).item()
+    assert saved["global_step"] == 3 and "DGP/layers/1/kern/patch_weights" in saved and "DGP/layers/0/feature/Z" in saved
+    flags2 = Mo.default_parser().parse_args(["-M", "8,8", "--feature-maps", "3", "--filter-sizes", "5,3", "--strides", "2,1",
+                                             "--batch-size", "8", "--num-samples", "2", "--load-model", "model"])
+    builder = Mo.ModelBuilder(flags2, X, Y, model_path=path, device=dev())
+    model2 = builder.build()
+    assert builder.global_step == 3
+    zs = model.draw_zs(8, 8, 0, step=11)
+    m1, v1 = model.predict_f(Xb, 2, zs=zs)
+    m2, v2 = model2.predict_f(Xb, 2, zs=zs)
+    np.testing.assert_allclose(npy(m2), npy(m1), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(npy(v2), npy(v1), rtol=1e-5, atol=1e-6)
