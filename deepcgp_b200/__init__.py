@@ -22,3 +22,4 @@ from .likelihoods import BroadcastingLikelihood, MultiClass  # noqa: E402,F401
 from .dgp import DGP_Base  # noqa: E402,F401
 from .grad import Adam, ElboGradient, TrainStep  # noqa: E402,F401
 from .models import ModelBuilder, save_model_parameters  # noqa: E402,F401
+from .experiment import Experiment, accuracy, exponential_decay, train_steps  # noqa: E402,F401

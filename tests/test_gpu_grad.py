@@ -197,3 +197,25 @@ def test_model_builder_checkpoint_roundtrip(tmp_path):
     m2, v2 = model2.predict_f(Xb, 2, zs=zs)
     np.testing.assert_allclose(npy(m2), npy(m1), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(npy(v2), npy(v1), rtol=1e-5, atol=1e-6)
+
+
+def test_experiment_driver_runs_and_logs(tmp_path):
+    """experiment.py:28-64 for --optimizer Adam: `test_every` iterations with the staircase learning rate, the accuracy
+    logger (utils/log.py:55-68) and the parameter dump."""
+    import argparse
+    import deepcgp_b200 as D
+    rng = np.random.RandomState(1)
+    X = rng.standard_normal((48, 12, 12, 1))
+    Y = rng.randint(0, 10, size=(48, 1))
+    flags = D.models.default_parser().parse_args(["-M", "8,8", "--feature-maps", "3", "--filter-sizes", "5,3", "--strides",
+                                                  "2,1", "--batch-size", "8", "--num-samples", "2", "--lr", "0.01"])
+    flags.name, flags.log_dir, flags.lr_decay_steps, flags.test_every, flags.optimizer = "exp", str(tmp_path), 4, 3, "Adam"
+    exp = D.Experiment(flags, X, Y, X_test=X[:40], Y_test=Y[:40], device=dev())
+    e1 = exp.train_step()
+    e2 = exp.train_step()
+    assert (e1["global_step"], e2["global_step"]) == (3, 6)
+    assert e1["lr"] == 0.01 and abs(e2["lr"] - 0.001) < 1e-12          # staircase: x0.1 after 4 steps
+    assert 0.0 <= e2["test_accuracy"] <= 1.0 and np.isfinite(e2["elbo"])
+    saved = np.load(str(tmp_path / "exp.npy"), allow_pickle=True).item()
+    assert saved["global_step"] == 6
+    np.testing.assert_allclose(saved["DGP/layers/0/q_mu"], npy(exp.model.layers[0].q_mu))

@@ -54,3 +54,16 @@ def test_checkpoint_keys_group_by_layer_and_shift_the_last_layer():
     assert lp[1]["base_kernel/variance"] == 4.0 and lp[1]["patch_weights"].shape == (16,)
     step, lp3 = Mo.load_layer_parameters(ck, 3)
     assert sorted(lp3) == [0, 2] and lp3[2]["Z"].shape == (5, 18)
+
+
+def test_learning_rate_schedule_and_step_count():
+    """experiment.py:72-73 (staircase decay x0.1 every lr_decay_steps) and arguments.py:4-7."""
+    import argparse
+    from deepcgp_b200 import experiment as E
+    assert E.exponential_decay(0.01, 0, 100000) == 0.01
+    assert E.exponential_decay(0.01, 99999, 100000) == 0.01
+    assert abs(E.exponential_decay(0.01, 100000, 100000) - 0.001) < 1e-15
+    assert abs(E.exponential_decay(0.01, 250000, 100000) - 0.0001) < 1e-15
+    assert abs(E.exponential_decay(0.01, 50000, 100000, staircase=False) - 0.01 * 0.1 ** 0.5) < 1e-15
+    f = argparse.Namespace(lr=0.01, lr_decay_steps=100000, test_every=50000)
+    assert E.train_steps(f) == 5            # log_0.1(5e-5/0.01) = 2.30 rounds of decay -> ceil(2.30 * 2)
