@@ -39,6 +39,9 @@ SIGNATURES = {
     "dcgp_launch_count": (C.c_longlong, []),
     "dcgp_set_kernel_timing": (None, [_i]),
     "dcgp_kernel_ms": (C.c_double, [_i]),
+    "dcgp_kernel_tensor_flops": (C.c_double, [_i]),
+    "dcgp_set_products": (None, [_i, _i, _i]),
+    "dcgp_get_products": (None, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dcgp_view_geometry": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dcgp_extract_patches": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dcgp_kuu": (_i, [_vp, _i, _i, _d, _d, _d, _vp, _vp]),
@@ -140,6 +143,20 @@ class Workspace:
             b = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._bufs[key] = b
         return b
+
+
+def products():
+    """(cond, dk, dq): split products per k-step of the three big T-sized GEMM families (dcgp_get_products)."""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    lib.dcgp_get_products(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def precision_string():
+    """The arithmetic the tensor-core path computes in, for bench.py's `dtype` field."""
+    cond, dk, dq = products()
+    return ("split-fp16 (hi+lo) operands on tcgen05, fp32 accumulate; products per k-step: a=Lm^-1k 3, G_r=C_r^T a %d, dK %d, dQ %d; "
+            "f64 M-only" % (cond, dk, dq))
 
 
 def raise_if_not_pd(info):

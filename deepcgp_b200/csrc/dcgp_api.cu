@@ -2,6 +2,10 @@
 // No device allocation happens here: every buffer comes from the caller; all work is stream-ordered.
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "dcgp_kernels.cuh"
 #include "dcgp_tc.cuh"
 
@@ -180,20 +184,23 @@ static int kl_terms(const F64Work& w, int white, const double* Lp, int ldp, cons
 struct AuxFork {
   cudaStream_t aux = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
 };
+// keyed by (device, calling stream); guarded by a mutex; never evicted (a process uses a handful of streams)
 static AuxFork& aux_for(cudaStream_t st) {
-  static AuxFork pool[8];
-  static cudaStream_t owner[8] = {nullptr};
-  static int used = 0;
-  for (int i = 0; i < used; ++i) if (owner[i] == st) return pool[i];
-  const int i = used < 8 ? used++ : 7;
-  owner[i] = st;
-  if (!pool[i].aux) {
-    cudaStreamCreateWithFlags(&pool[i].aux, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&pool[i].fork, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&pool[i].join, cudaEventDisableTiming);
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, AuxFork> pool;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  AuxFork& a = pool[std::make_pair(dev, st)];
+  if (!a.ok) {
+    a.ok = cudaStreamCreateWithFlags(&a.aux, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!a.ok) set_error("auxiliary stream / events: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  return pool[i];
+  return a;
 }
 
 static int check_desc(const dcgp_layer_desc* d) {
@@ -216,6 +223,14 @@ int dcgp_version(void) { return 100; }
 long long dcgp_launch_count(void) { return dcgp::launch_count(); }
 void dcgp_set_kernel_timing(int on) { dcgp::tc_set_timing(on); }
 double dcgp_kernel_ms(int which) { return dcgp::tc_kernel_ms(which); }
+double dcgp_kernel_tensor_flops(int which) { return dcgp::tc_kernel_flops(which); }
+void dcgp_set_products(int cond, int dk, int dq) { dcgp::tc_set_products(cond, dk, dq); }
+void dcgp_get_products(int* cond, int* dk, int* dq) {
+  const dcgp::TcProducts& t = dcgp::tc_products();
+  if (cond) *cond = t.cond;
+  if (dk) *dk = t.dk;
+  if (dq) *dq = t.dq;
+}
 
 int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH, int* OW, int* P, int* L) {
   if (H < f || W < f || f < 1 || s < 1 || C < 1) { set_error("bad view geometry"); return DCGP_ERR_ARG; }
@@ -351,14 +366,16 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
   const double* Lp = w.Kuu;        // Cholesky factor of the prior covariance and its inverse
   const double* Lpinv = w.Linv;
   double* Kp = w.Wr;               // scratch that is free at this point on both paths
+  AuxFork* ax = nullptr;
   if (own_prior) {                 // forked: runs concurrently with the Kuu chain below
-    AuxFork& ax = aux_for(st);
-    cudaEventRecord(ax.fork, st);
-    cudaStreamWaitEvent(ax.aux, ax.fork, 0);
-    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, Kp, ax.aux));
-    DCGP_TRY(potrf_f64(Kp, M, M, w.invDp, info, ax.aux));
-    DCGP_TRY(trtri_f64(Kp, M, M, w.invDp, w.Lpinv, w.trws2, ax.aux));
-    cudaEventRecord(ax.join, ax.aux);
+    ax = &aux_for(st);
+    if (!ax->ok) return DCGP_ERR_CUDA;
+    cudaEventRecord(ax->fork, st);
+    cudaStreamWaitEvent(ax->aux, ax->fork, 0);
+    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, Kp, ax->aux));
+    DCGP_TRY(potrf_f64(Kp, M, M, w.invDp, info, ax->aux));
+    DCGP_TRY(trtri_f64(Kp, M, M, w.invDp, w.Lpinv, w.trws2, ax->aux));
+    cudaEventRecord(ax->join, ax->aux);
     Lp = Kp;
     Lpinv = w.Lpinv;
   }
@@ -389,7 +406,7 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
       g.C = w.Kinv; g.ldc = M; g.alpha = 1.0; g.batch = 1;
       DCGP_TRY(gemm_f64(g, st));
     }
-    if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
+    if (own_prior) cudaStreamWaitEvent(st, ax->join, 0);
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
                                w.beta, w.sc + 1, w.Kinv, 2, 1, alpha, st));
     return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
@@ -410,12 +427,12 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
                                w.beta, w.sc + 1, w.Kinv, 1, 0, nullptr, st));
     DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
     if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
-    if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
+    if (own_prior) cudaStreamWaitEvent(st, ax->join, 0);
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
                                w.beta, w.sc + 1, w.Kinv, 2, 0, nullptr, st));
     return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
   }
-  if (own_prior) cudaStreamWaitEvent(st, aux_for(st).join, 0);
+  if (own_prior) cudaStreamWaitEvent(st, ax->join, 0);
   if (own_prior) {   // the fp64 path needs w.Wr for W_r first: move the prior factor out of the way
     cudaMemcpyAsync(w.Kinv == gi.G ? w.tmpK : w.Kinv, Kp, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToDevice, st);
     Lp = (w.Kinv == gi.G) ? w.tmpK : w.Kinv;

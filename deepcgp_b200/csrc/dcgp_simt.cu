@@ -5,6 +5,8 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <mutex>
+
 #include "dcgp_kernels.cuh"
 
 namespace dcgp {
@@ -268,6 +270,7 @@ int launch_cond_simt(const float* Kt, int T, int ld, int Mp, const float* W, con
 // ------------------------------------------------------------------------------------------ finalize (+ a8 sample)
 // var[t,r] = Knn(t) - acc[t,0] + acc[t,1+r]   (conditionals.py:40,65),  output layouts of layers.py:128-131,
 // then DS/utils.py:41: sample = mean + z * sqrt(var + jitter).  `n_rep` replicates rows (DS/dgp.py:63).
+constexpr float kVarFloor = 1e-12f;   // floor of var + jitter under the square root (reparameterised sample and its gradient)
 __global__ void finalize_kernel(const float* __restrict__ acc, const float* __restrict__ mean_t, int T, int R,
                                 float knn_const, const float* __restrict__ knn_vec, int n_rep,
                                 const float* __restrict__ z, float jitter, float* __restrict__ mean,
@@ -282,7 +285,9 @@ __global__ void finalize_kernel(const float* __restrict__ acc, const float* __re
     const float v = knn - acc[(long long)t * (R + 1)] + acc[(long long)t * (R + 1) + 1 + r];
     mean[e] = m;
     var[e] = v;
-    if (sample) sample[e] = m + z[e] * sqrtf(v + jitter);
+    // The float64 reference cannot see var + jitter < 0; the fp32-class variance can (cancellation of size ~1e-4 sigma^2
+    // against a true variance ~ 0): clamp the argument of the square root only, `var` is reported as computed.
+    if (sample) sample[e] = m + z[e] * sqrtf(fmaxf(v + jitter, kVarFloor));
   }
 }
 int launch_finalize(const float* acc, const float* mean_t, int T, int R, float knn_const, const float* knn_vec,
@@ -314,7 +319,7 @@ int launch_finalize_ref_layout(const float* acc, const float* Knn, int P, int N,
 __global__ void reparam_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ z,
                                size_t n, float jitter, float* __restrict__ out) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
-    out[e] = mean[e] + z[e] * sqrtf(var[e] + jitter);
+    out[e] = mean[e] + z[e] * sqrtf(fmaxf(var[e] + jitter, kVarFloor));
 }
 int launch_reparam(const float* mean, const float* var, const float* z, size_t n, float jitter, float* out, cudaStream_t st) {
   reparam_kernel<<<148 * 8, 256, 0, st>>>(mean, var, z, n, jitter, out);
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(128) varexp_kernel(const float* __restrict__ F
                                                      double logepsk, double* __restrict__ varexp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= SN) return;
-  const int y = Y[i % N];
+  const int y = min(max(Y[i % N], 0), K - 1);   // labels are validated by the host (likelihoods.py); never index out of range
   double mu[16], isd[16];
   for (int k = 0; k < K; ++k) {
     mu[k] = (double)Fmu[(long long)i * K + k];
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(128) varexp_grad_kernel(const float* __restric
                                                           double coef, float* __restrict__ gmu, float* __restrict__ gvar) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= SN) return;
-  const int y = Y[i % N];
+  const int y = min(max(Y[i % N], 0), K - 1);   // labels are validated by the host (likelihoods.py); never index out of range
   double mu[16], isd[16], vk[16], dmu[16], dv[16];
   bool vclip[16];
   for (int k = 0; k < K; ++k) {
@@ -590,7 +595,8 @@ __global__ void sample_backward_kernel(const float* __restrict__ gF, const float
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
     const float g = gF[e];
     g_mean[e] = g;
-    g_var[e] = g * z[e] * 0.5f * rsqrtf(var[e] + jitter);
+    const float sv = var[e] + jitter;      // where the forward clamped the square root the sample does not depend on var
+    g_var[e] = sv > kVarFloor ? g * z[e] * 0.5f * rsqrtf(sv) : 0.f;
   }
 }
 int launch_sample_backward(const float* gF, const float* z, const float* var, size_t n, float jitter, float* g_mean, float* g_var,
@@ -661,30 +667,27 @@ int launch_varexp_grad(const float* Fmu, const float* Fvar, const int32_t* Y, in
 }
 
 static void init_gh() {
-  static bool init = false;
-  if (!init) {
-    double x[20], w[20];
-    gauss_hermite_20(x, w);
-    for (int i = 0; i < 20; ++i) w[i] /= sqrt(M_PI);
-    cudaMemcpyToSymbol(c_gh_x, x, sizeof(x));
-    cudaMemcpyToSymbol(c_gh_w, w, sizeof(w));
-    init = true;
+  // __constant__ memory is per device: load the tables once for every device this process uses
+  static std::mutex mu;
+  static bool done[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  double x[20], w[20];
+  gauss_hermite_20(x, w);
+  for (int i = 0; i < 20; ++i) w[i] /= sqrt(M_PI);
+  if (cudaMemcpyToSymbol(c_gh_x, x, sizeof(x)) != cudaSuccess || cudaMemcpyToSymbol(c_gh_w, w, sizeof(w)) != cudaSuccess) {
+    set_error("Gauss-Hermite tables: %s", cudaGetErrorString(cudaGetLastError()));
+    return;
   }
+  done[dev] = true;
 }
 
 int launch_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon, double* varexp,
                   double* sum, cudaStream_t st) {
   if (K > 16 || K < 2) { set_error("varexp: K must be in [2,16]"); return DCGP_ERR_ARG; }
   init_gh();
-  static bool init = true;
-  if (!init) {
-    double x[20], w[20];
-    gauss_hermite_20(x, w);
-    for (int i = 0; i < 20; ++i) w[i] /= sqrt(M_PI);
-    cudaMemcpyToSymbol(c_gh_x, x, sizeof(x));
-    cudaMemcpyToSymbol(c_gh_w, w, sizeof(w));
-    init = true;
-  }
   const int SN = S * N;
   varexp_kernel<<<ceil_div(SN, 128), 128, 0, st>>>(Fmu, Fvar, Y, SN, N, K, log(1.0 - epsilon), log(epsilon / (K - 1.0)), varexp);
   sum_f64_kernel<<<1, 1024, 0, st>>>(varexp, SN, sum);

@@ -13,6 +13,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "dcgp_tc.cuh"
 
 namespace dcgp {
@@ -157,6 +159,8 @@ constexpr int MODE_A = 2;      // chained form, first stage: a = K Lm^-T (lower-
 struct TcParams {
   int n_items;
   int nkb;        // K-dimension blocks of 64
+  int nprod;      // split products per k-step: 3 = Al*Bh + Ah*Bl + Ah*Bh (22-bit operands), 2 = Al*Bh + Ah*Bh (A 22 bits, B 11),
+                  // 1 = Ah*Bh (11-bit operands); the planes that are not multiplied are not loaded either
   int bf16;       // MODE_GEMM: operand planes are bf16 (hi + lo) instead of fp16
   // ---- MODE_COND
   int T;          // valid patch-columns
@@ -230,25 +234,56 @@ __device__ __forceinline__ void item_krange(const TcParams& p, int item, int jt,
   }
 }
 
+// Triangular operands at 64-column granularity.  A k-block that straddles the diagonal of the B operand only multiplies the
+// accumulator columns whose B rows are not structurally zero: the MMA is issued with N = n (64 .. BN) on the B rows / TMEM
+// columns [col_off, col_off + n), and only those rows are loaded.  The k-blocks of a tile are walked so that the FIRST one is
+// full width (it initialises all BN accumulator columns): ascending for MODE_A (Lm^-1 lower triangular), descending for the
+// C_r^T blocks of MODE_COND (upper triangular).
+template <int MODE, int BN>
+__device__ __forceinline__ bool tile_descending(const TcParams& p, int item) {
+  if (MODE != MODE_COND || p.tri != 2) return false;
+  const int per = p.R + 2 - p.blk_first;
+  return item % per != per - 1;
+}
+template <int MODE, int BN>
+__device__ __forceinline__ void kb_cols(const TcParams& p, bool desc, int jt, int kb, int& col_off, int& n) {
+  col_off = 0; n = BN;
+  if (MODE == MODE_A) { col_off = max(0, kb * kBK - jt * BN); n = BN - col_off; }
+  if (MODE == MODE_COND && desc) n = min(BN, kb * kBK + kBK - jt * BN);
+}
+constexpr int kMaxStages = 8;
+// ring geometry for a given number of split products (the ring always owns Cfg::kStages * Cfg::kStageBytes of shared memory)
+template <int BN>
+__device__ __forceinline__ void ring_geom(int nprod, int& a_planes, int& b_planes, int& stage_bytes, int& n_stages) {
+  using Cfg = CondCfg<BN>;
+  a_planes = nprod >= 2 ? 2 : 1;
+  b_planes = nprod >= 3 ? 2 : 1;
+  stage_bytes = a_planes * Cfg::kStageA + b_planes * Cfg::kStageB;
+  n_stages = min(kMaxStages, (Cfg::kStages * Cfg::kStageBytes) / stage_bytes);
+}
+
 template <int MODE, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo, TcParams p) {
+          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+          const __grid_constant__ CUtensorMap tmB64_hi, const __grid_constant__ CUtensorMap tmB64_lo, TcParams p) {
   using Cfg = CondCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-B alignment
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full = empty_bar + Cfg::kStages;   // [2]
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = empty_bar + kMaxStages;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;             // [2]
   uint32_t* tmem_base_smem = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = p.nkb;
+  int a_planes, b_planes, stage_bytes, n_stages;
+  ring_geom<BN>(p.nprod, a_planes, b_planes, stage_bytes, n_stages);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA_hi); tma_prefetch_desc(&tmA_lo); tma_prefetch_desc(&tmB_hi); tma_prefetch_desc(&tmB_lo);
-    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    tma_prefetch_desc(&tmB64_hi); tma_prefetch_desc(&tmB64_lo);
+    for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
     fence_barrier_init();
     fence_proxy_async();
@@ -265,19 +300,31 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int njt = tiles_in_item<MODE, BN>(p, item);
+        const bool desc = tile_descending<MODE, BN>(p, item);
         for (int jt = 0; jt < njt; ++jt) {
           int arow, brow, kb0, kb1;
           tile_rows<MODE, BN>(p, item, jt, arow, brow);
           item_krange<MODE, BN>(p, item, jt, kb0, kb1);
-          for (int kb = kb0; kb < kb1; ++kb) {
+          for (int i = 0; i < kb1 - kb0; ++i) {
+            const int kb = desc ? kb1 - 1 - i : kb0 + i;
+            int col_off, n;
+            kb_cols<MODE, BN>(p, desc, jt, kb, col_off, n);
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * Cfg::kStageBytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            uint8_t* st = smem + stage * stage_bytes;
+            uint8_t* sb = st + a_planes * Cfg::kStageA;
+            mbar_expect_tx(&full_bar[stage], a_planes * Cfg::kStageA + b_planes * n * (kBK * 2));
             tma_load_2d(st, &tmA_hi, &full_bar[stage], kb * kBK, arow);
-            tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, arow);
-            tma_load_2d(st + 2 * Cfg::kStageA, &tmB_hi, &full_bar[stage], kb * kBK, brow);
-            tma_load_2d(st + 2 * Cfg::kStageA + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb * kBK, brow);
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            if (a_planes == 2) tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, arow);
+            if (n == BN) {
+              tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kBK, brow);
+              if (b_planes == 2) tma_load_2d(sb + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb * kBK, brow);
+            } else {                                   // partial block: 64-row boxes of the non-zero rows only
+              for (int c = col_off; c < col_off + n; c += 64) {
+                tma_load_2d(sb + c * (kBK * 2), &tmB64_hi, &full_bar[stage], kb * kBK, brow + c);
+                if (b_planes == 2) tma_load_2d(sb + Cfg::kStageB + c * (kBK * 2), &tmB64_lo, &full_bar[stage], kb * kBK, brow + c);
+              }
+            }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -285,24 +332,30 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(BN) | (p.bf16 ? kIdescBf16 : 0u);
+      const uint32_t idesc0 = (make_idesc_f16(BN) & ~(0x3Fu << 17)) | (p.bf16 ? kIdescBf16 : 0u);
       int stage = 0; uint32_t phase = 0;
       uint32_t tile = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int njt = tiles_in_item<MODE, BN>(p, item);
+        const bool desc = tile_descending<MODE, BN>(p, item);
         for (int jt = 0; jt < njt; ++jt, ++tile) {
           const uint32_t buf = tile & 1, use = tile >> 1;
           mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * BN;
           int kb0, kb1;
           item_krange<MODE, BN>(p, item, jt, kb0, kb1);
-          for (int kb = kb0; kb < kb1; ++kb) {
+          uint32_t acc = 0;                               // the first MMA of the tile overwrites the accumulator
+          for (int i = 0; i < kb1 - kb0; ++i) {
+            const int kb = desc ? kb1 - 1 - i : kb0 + i;
+            int col_off, n;
+            kb_cols<MODE, BN>(p, desc, jt, kb, col_off, n);
+            const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
+            const uint32_t d_tmem = tmem_base + buf * BN + col_off;
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
             const uint32_t a_lo = a_hi + Cfg::kStageA;
-            const uint32_t b_hi = a_hi + 2 * Cfg::kStageA;
+            const uint32_t b_hi = a_hi + a_planes * Cfg::kStageA + col_off * (kBK * 2);
             const uint32_t b_lo = b_hi + Cfg::kStageB;
             const uint64_t dah = make_sw128_desc(a_hi), dal = make_sw128_desc(a_lo);
             const uint64_t dbh = make_sw128_desc(b_hi), dbl = make_sw128_desc(b_lo);
@@ -310,12 +363,13 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
             for (int k = 0; k < kBK / 16; ++k) {
               const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // advance 32 bytes inside the swizzle atom
               // small cross terms first, dominant term last
-              umma_f16(d_tmem, dal + koff, dbh + koff, idesc, (kb != kb0) || (k != 0));
-              umma_f16(d_tmem, dah + koff, dbl + koff, idesc, 1);
-              umma_f16(d_tmem, dah + koff, dbh + koff, idesc, 1);
+              if (a_planes == 2) { umma_f16(d_tmem, dal + koff, dbh + koff, idesc, acc); acc = 1; }
+              if (b_planes == 2) { umma_f16(d_tmem, dah + koff, dbl + koff, idesc, acc); acc = 1; }
+              umma_f16(d_tmem, dah + koff, dbh + koff, idesc, acc);
+              acc = 1;
             }
             umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-            if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(&tmem_full[buf]);                     // accumulator complete -> epilogue
         }
@@ -529,11 +583,38 @@ double tc_kernel_ms(int which) {
   if (cudaEventElapsedTime(&ms, g_ev[which][0], g_ev[which][1]) != cudaSuccess) return -1.0;
   return (double)ms;
 }
+static double g_flops[kTimers] = {0, 0, 0, 0};   // executed tensor-pipe flops of the last timed launch(es) of each kind
+double tc_kernel_flops(int which) { return (which >= 0 && which < kTimers) ? g_flops[which] : 0.0; }
 struct ScopedTimer {
   int which; cudaStream_t st; bool on;
   ScopedTimer(int w, cudaStream_t s) : which(w), st(s), on(g_timing && g_ev_init) { if (on) cudaEventRecord(g_ev[which][0], st); }
+  void flops(double f) { if (on) g_flops[which] = f; }
   ~ScopedTimer() { if (on) { cudaEventRecord(g_ev[which][1], st); g_ev_used[which] = true; } }
 };
+
+// How many of the three split products each T-sized GEMM family issues (see TcParams::nprod).  The first stage of the
+// conditional (a = Lm^-1 k: cancellation) and the small GEMMs always use 3.  Defaults can be overridden with
+// DCGP_PROD_COND / DCGP_PROD_DK / DCGP_PROD_DQ or dcgp_set_products().
+static TcProducts g_prod = {0, 0, 0};
+static int env_prod(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int v = e ? atoi(e) : dflt;
+  return (v >= 1 && v <= 3) ? v : dflt;
+}
+const TcProducts& tc_products() {
+  if (!g_prod.cond) {
+    g_prod.cond = env_prod("DCGP_PROD_COND", kDefaultProdCond);
+    g_prod.dk = env_prod("DCGP_PROD_DK", kDefaultProdDk);
+    g_prod.dq = env_prod("DCGP_PROD_DQ", kDefaultProdDq);
+  }
+  return g_prod;
+}
+void tc_set_products(int cond, int dk, int dq) {
+  tc_products();
+  if (cond >= 1 && cond <= 3) g_prod.cond = cond;
+  if (dk >= 1 && dk <= 3) g_prod.dk = dk;
+  if (dq >= 1 && dq <= 3) g_prod.dq = dq;
+}
 
 static int num_sms() {
   static int n = 0;
@@ -552,8 +633,9 @@ static size_t w_rows(int Mp, int R) { return (size_t)(R + 1) * Mp + kWPadRows; }
 
 template <int MODE, int BN>
 static int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl,
-                     const TcParams& p, cudaStream_t st) {
+                     const CUtensorMap& tmB64h, const CUtensorMap& tmB64l, const TcParams& p, cudaStream_t st) {
   using Cfg = CondCfg<BN>;
+  if (p.nprod < 1 || p.nprod > 3) { set_error("tc_kernel: nprod must be 1, 2 or 3"); return DCGP_ERR_ARG; }
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -562,7 +644,7 @@ static int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUt
   }
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   if (grid <= 0) return DCGP_OK;
-  tc_kernel<MODE, BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmAh, tmAl, tmBh, tmBl, p);
+  tc_kernel<MODE, BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmAh, tmAl, tmBh, tmBl, tmB64h, tmB64l, p);
   return check_launch("tc_kernel");
 }
 
@@ -579,8 +661,10 @@ static int launch_cond_tc(const TcPrep& prep, const TcCondWork& w, int T, int Mp
   p.T = T; p.Mp = Mp; p.R = R; p.njt = Mp / BN; p.nkb = Mp / kBK;
   p.n_items = ceil_div(T, kBM) * (R + 2);
   p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
+  p.nprod = 3;
   ScopedTimer timer(0, st);
-  return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, p, st);
+  timer.flops(3 * 2.0 * (double)w.Tpad * ((double)(R + 1) * Mp + BN) * Mp);
+  return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, tmBh, tmBl, p, st);
 }
 
 __global__ void set_scale_kernel(float bound, float* __restrict__ scal2);
@@ -598,7 +682,7 @@ bool tc_forward_chained() {
 template <int BN>
 static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc,
                                float* mean, cudaStream_t st) {
-  CUtensorMap tmKh, tmKl, tmAh, tmAl, tmBh, tmBl;
+  CUtensorMap tmKh, tmKl, tmAh, tmAl, tmBh, tmBl, tmB64h, tmB64l;
   int rc;
   if ((rc = make_tmap_f16(&tmKh, w.Kh, w.Tpad, Mp, kBM))) return rc;
   if ((rc = make_tmap_f16(&tmKl, w.Kl, w.Tpad, Mp, kBM))) return rc;
@@ -606,19 +690,30 @@ static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, i
   if ((rc = make_tmap_f16(&tmAl, w.Al, w.Tpad, Mp, kBM))) return rc;
   if ((rc = make_tmap_f16(&tmBh, prep.Wh, w_rows(Mp, R), Mp, BN))) return rc;
   if ((rc = make_tmap_f16(&tmBl, prep.Wl, w_rows(Mp, R), Mp, BN))) return rc;
+  if ((rc = make_tmap_f16(&tmB64h, prep.Wh, w_rows(Mp, R), Mp, 64))) return rc;
+  if ((rc = make_tmap_f16(&tmB64l, prep.Wl, w_rows(Mp, R), Mp, 64))) return rc;
   set_scale_kernel<<<1, 1, 0, st>>>(sqrtf(a_bound), w.ascal);
   if ((rc = check_launch("set_scale"))) return rc;
   ScopedTimer timer(0, st);
+  const int nprod2 = tc_products().cond;
+  {   // executed tensor flops of the two launches: 64-column granularity on the triangular operands
+    const int nb = Mp / kBK;                                   // 64-blocks per side
+    const double tri_blocks = 0.5 * nb * (nb + 1);             // (k-block, 64-column block) pairs that are not structurally zero
+    const double per_blk = 2.0 * (double)w.Tpad * kBK * kBK;   // one 64 x 64 block pair over all patch columns
+    timer.flops(3 * per_blk * tri_blocks + nprod2 * (per_blk * tri_blocks * R + 2.0 * (double)w.Tpad * BN * Mp));
+  }
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.Mp = Mp; p.R = R; p.njt = Mp / BN; p.nkb = Mp / kBK;
   p.n_items = ceil_div(T, kBM);
   p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
   p.Ah_out = (__half*)w.Ah; p.Al_out = (__half*)w.Al; p.ascal = w.ascal;
-  if ((rc = launch_tc<MODE_A, BN>(tmKh, tmKl, tmBh, tmBl, p, st))) return rc;
+  p.nprod = 3;                                                 // a = Lm^-1 k cancels: always the full 22-bit product
+  if ((rc = launch_tc<MODE_A, BN>(tmKh, tmKl, tmBh, tmBl, tmB64h, tmB64l, p, st))) return rc;
   p.n_items = ceil_div(T, kBM) * (R + 1);
   p.blk_first = 1; p.tri = 2; p.kscal = w.ascal;
-  return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, p, st);
+  p.nprod = nprod2;                                            // G_r = C_r^T a feeds a sum of squares (no cancellation)
+  return launch_tc<MODE_COND, BN>(tmAh, tmAl, tmBh, tmBl, tmB64h, tmB64l, p, st);
 }
 
 int tc_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc, float* mean,
@@ -654,9 +749,10 @@ int tc_gemm(const TcGemm& g, cudaStream_t st) {
   p.m_valid = g.m; p.n_valid = g.n;
   p.a_scal = g.a_scal; p.b_scal = g.b_scal;
   p.C = g.C; p.c_batch_stride = g.c_batch_stride; p.ldc = g.ldc; p.sq_out = g.sq_out;
-  if (BN == 256) return launch_tc<MODE_GEMM, 256>(tmAh, tmAl, tmBh, tmBl, p, st);
-  if (BN == 128) return launch_tc<MODE_GEMM, 128>(tmAh, tmAl, tmBh, tmBl, p, st);
-  return launch_tc<MODE_GEMM, 64>(tmAh, tmAl, tmBh, tmBl, p, st);
+  p.nprod = g.nprod ? g.nprod : 3;
+  if (BN == 256) return launch_tc<MODE_GEMM, 256>(tmAh, tmAl, tmBh, tmBl, tmBh, tmBl, p, st);
+  if (BN == 128) return launch_tc<MODE_GEMM, 128>(tmAh, tmAl, tmBh, tmBl, tmBh, tmBl, p, st);
+  return launch_tc<MODE_GEMM, 64>(tmAh, tmAl, tmBh, tmBl, tmBh, tmBl, p, st);
 }
 
 int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st) {

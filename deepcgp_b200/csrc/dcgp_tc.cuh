@@ -68,6 +68,7 @@ struct TcGemm {
   float* absmax_out;                             // optional: atomic max |C| (zero it first)
   int bf16;                                      // planes are bf16 hi/lo (unscaled values allowed) instead of fp16
   int splits; long long c_split_stride;          // split-K: partial C per split (caller reduces); splits <= 1 = off
+  int nprod;                                     // split products per k-step (0 = 3)
 };
 size_t tc_bgemm_workspace_bytes(int batch, int m, int n, int k);
 int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride, long long b_bstride,
@@ -89,6 +90,13 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
 
 void tc_set_timing(int on);
 double tc_kernel_ms(int which);   // 0 = conditional GEMM, 1 = Kuf, 2 = dK (+dd) GEMM, 3 = dQ GEMM (last launch of each)
+double tc_kernel_flops(int which);   // executed tensor-pipe flops of that launch (counted by the launcher)
+
+// split products per k-step of the three big T-sized GEMM families (1..3, see TcParams::nprod in dcgp_tc.cu)
+struct TcProducts { int cond, dk, dq; };
+constexpr int kDefaultProdCond = 3, kDefaultProdDk = 3, kDefaultProdDq = 3;
+const TcProducts& tc_products();
+void tc_set_products(int cond, int dk, int dq);   // 0 leaves a value unchanged
 
 // Workspace of the backward pass of one layer (see dcgp_tc_bwd.inc)
 struct TcBwdWork {

@@ -90,9 +90,11 @@ class DGP_Base(object):
         idx = self._mb.next_indices()
         return self.X_all[idx], self.Y_all[idx]
 
-    def _build_likelihood(self, X=None, Y=None, zs=None, n_global=None, keep=False):
+    def _build_likelihood(self, X=None, Y=None, zs=None, n_global=None, keep=False, defer_sum=False):
         """DS/dgp.py:92-98: ELBO = sum_n E_q[log p(y_n|f_n)] * num_data/batch - sum_l KL_l, as a device scalar.
-        The whole step stays on the stream; nothing is read back here."""
+        The whole step stays on the stream; nothing is read back here.
+        defer_sum (grad.TrainStep, image-sharded): leave this rank's data term in self._sum and skip the ELBO kernel -- the
+        caller folds the sum into its gradient all-reduce and calls _finish_elbo() afterwards (no collective mid-step)."""
         if X is None:
             X, Y = self._next_batch()
         X = _lib.f32(X, self.device)
@@ -108,6 +110,8 @@ class DGP_Base(object):
             layer._hold = True
             if layer._pending is not None:      # grad.TrainStep pipelines this layer's update + prepare(); it is
                 continue                        # completed lazily, right before the layer is applied
+            if layer._fresh and layer._ready is not None:
+                continue                        # TrainStep.finish() already queued the prepare for these parameters
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 layer.prepare()
@@ -127,10 +131,19 @@ class DGP_Base(object):
             for layer in self.layers:
                 layer._hold = False
                 layer._ready = None
+                layer._fresh = False
+        self._elbo_args = (S, float(self.num_data), float(n_global or N))
+        if defer_sum:
+            return self._elbo[0]
         if n_global is not None and n_global != N:
             allreduce_sum_(self._sum)        # image-sharded step: the data term is a sum over all ranks' images
-        _lib.check(_lib.lib.dcgp_elbo(_lib.ptr(self._sum), S, float(self.num_data), float(n_global or N),
-                                      _lib.ptr(self._kls), len(self.layers), _lib.ptr(self._elbo), _lib.stream()))
+        return self._finish_elbo()
+
+    def _finish_elbo(self):
+        """ELBO scalar from self._sum (already summed over ranks) and the KLs, on the current stream."""
+        S, num_data, n = self._elbo_args
+        _lib.check(_lib.lib.dcgp_elbo(_lib.ptr(self._sum), S, num_data, n, _lib.ptr(self._kls), len(self.layers),
+                                      _lib.ptr(self._elbo), _lib.stream()))
         return self._elbo[0]
 
     # ------------------------------------------------------------------ DS/dgp.py:100-126 (autoflow methods)

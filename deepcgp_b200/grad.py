@@ -290,7 +290,7 @@ class ElboGradient(object):
         self.bwd = [LayerBackward(l) for l in model.layers]
         self._side = None
 
-    def _forward(self, X, Y, zs, n_global):
+    def _forward(self, X, Y, zs, n_global, defer_sum=False):
         """Forward ELBO (layer outputs kept) and the gradient of the data term w.r.t. the last layer's mean / var."""
         model = self.model
         X = _lib.f32(X, model.device)
@@ -301,11 +301,11 @@ class ElboGradient(object):
             n0 = shard_range(n_g, rank, wsize)[0] if n_g != N else 0
             zs = model.draw_zs(N, n_g, n0)
         zs = [_lib.f32(z, model.device) for z in zs]
-        elbo = model._build_likelihood(X, Y, zs=zs, n_global=n_global, keep=True)
+        elbo = model._build_likelihood(X, Y, zs=zs, n_global=n_global, keep=True, defer_sum=defer_sum)
         Fs, Fmeans, Fvars = model._fwd
         K = Fmeans[-1].shape[2]
         coef = float(model.num_data) / float(n_global or N) / S
-        Yd = torch.as_tensor(Y, device=model.device).reshape(-1).to(torch.int32).contiguous()
+        Yd = model.likelihood.likelihood._labels(Y, model.device)
         Fm, Fv = Fmeans[-1].reshape(S * N, K).contiguous(), Fvars[-1].reshape(S * N, K).contiguous()
         g_mean, g_var = torch.empty_like(Fm), torch.empty_like(Fv)
         lik = model.likelihood.likelihood
@@ -429,6 +429,7 @@ class Adam(object):
                 layer.q_sqrt = src
             else:
                 layer.kern.patch_weights = src
+            layer._fresh = False            # any prepare() queued before this point is for the old parameters
         # kernel hyper-parameters travel by value in dcgp_layer_desc: ONE host read-back per step for all layers
         vals = torch.nn.functional.softplus(torch.cat([s for _, _, s in hyp])) + 1e-6
         vals = vals.cpu().tolist()
@@ -462,14 +463,35 @@ class Adam(object):
         assert hyp[0][1] == "variance" and hyp[1][2] == hyp[0][2] + 1
         return self.flat[hyp[0][2]:hyp[0][2] + 2]
 
-    def step_layer(self, li, grads, step_no):
+    def _allreduce_slice(self, lo, hi, extra=None):
+        """Sum self.grad[lo:hi] over the ranks (current stream).  The exchange is a single float32 bucket (the
+        flat gradient travels as fp32; the optimiser state stays float64); `extra` (a 1-element float64 tensor, e.g. the
+        ELBO's data term) rides in the bucket's last slot and is reduced in place with it."""
+        _, wsize = world()
+        if wsize == 1:
+            return
+        key = (lo, hi)
+        if not hasattr(self, "_buckets"):
+            self._buckets = {}
+        b = self._buckets.get(key)
+        if b is None:
+            b = self._buckets[key] = torch.zeros(hi - lo + 1, dtype=torch.float32, device=self.grad.device)
+        b[:hi - lo].copy_(self.grad[lo:hi])
+        if extra is not None:
+            b[hi - lo:].copy_(extra)
+        allreduce_sum_(b)
+        self.grad[lo:hi].copy_(b[:hi - lo])
+        if extra is not None:
+            extra.copy_(b[hi - lo:])
+
+    def step_layer(self, li, grads, step_no, extra=None):
         """Adam update of layer li's slice on the CURRENT stream; returns (pinned host tensor, event) of the layer's
         constrained (variance, lengthscale) -- they travel by value in dcgp_layer_desc, so the host needs them back.
         grads=None: the layer's slice of self.grad has already been filled (captured graph)."""
         if grads is not None:
             self._store_grads(grads, li)
         lo, hi = self.layer_range(li)
-        allreduce_sum_(self.grad[lo:hi])
+        self._allreduce_slice(lo, hi, extra)
         _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat[lo:hi]), _lib.ptr(self.grad[lo:hi]), _lib.ptr(self.m[lo:hi]),
                                       _lib.ptr(self.v[lo:hi]), hi - lo, self.lr, self.b1, self.b2, self.eps, step_no, 1,
                                       _lib.stream()))
@@ -491,7 +513,7 @@ class Adam(object):
     def step(self, grads):
         """grads: list (per layer) of dicts of d ELBO / d constrained parameter (this rank's share)."""
         self._store_grads(grads)
-        allreduce_sum_(self.grad)                                       # the single exchange of the image-sharded step
+        self._allreduce_slice(0, self.n)                                # the single exchange of the image-sharded step
         self.step_no += 1
         _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v), self.n,
                                       self.lr, self.b1, self.b2, self.eps, self.step_no, 1, _lib.stream()))
@@ -569,9 +591,10 @@ class TrainStep(object):
 
         self._graphed("dynamic", i, run)
 
-    def _chain(self, i, wsize):
+    def _chain(self, i, wsize, with_elbo=False):
         """Queue layer i's M-only chain rule + Adam slice on its side stream and leave the rest (hyper-parameter read-back,
-        prepare for the next step) as the layer's pending hook."""
+        prepare for the next step) as the layer's pending hook.  with_elbo: this layer's gradient bucket also carries the
+        ELBO's data term (image-sharded runs), and the ELBO scalar is formed behind it on the same stream."""
         model, eg, opt = self.model, self.eg, self.opt
         layer = model.layers[i]
         main = torch.cuda.current_stream(model.device)
@@ -583,7 +606,11 @@ class TrainStep(object):
             if not self.early_static:
                 self._m_only_static(i, wsize)
             self._m_only_to_grad(i, wsize)
-            host, ev = opt.step_layer(i, None, opt.step_no)
+            host, ev = opt.step_layer(i, None, opt.step_no, extra=model._sum if with_elbo else None)
+            if with_elbo:
+                model._finish_elbo()
+                self._elbo_ready = torch.cuda.Event()
+                self._elbo_ready.record(side)
 
         def finish():
             ev.synchronize()
@@ -593,15 +620,19 @@ class TrainStep(object):
                 layer.prepare()
                 layer._ready = torch.cuda.Event()
                 layer._ready.record(side)
+            layer._fresh = True          # consumed (and cleared) by the next forward pass
 
         layer._pending = finish
 
     def __call__(self, X, Y, zs=None, n_global=None):
         model, eg, opt = self.model, self.eg, self.opt
-        X, zs, elbo, g_mean, g_var = eg._forward(X, Y, zs, n_global)
+        _, wsize = world()
+        sharded = wsize > 1 and n_global is not None and int(n_global) != int(X.shape[0])
+        # image-sharded: the data term of the ELBO is summed over the ranks inside layer 0's gradient bucket (no separate
+        # collective between the forward and the backward pass)
+        X, zs, elbo, g_mean, g_var = eg._forward(X, Y, zs, n_global, defer_sum=sharded)
         Fs = model._fwd[0]
         N, S = X.shape[0], model.num_samples
-        _, wsize = world()
         nl = len(model.layers)
         opt.step_no += 1
         main = torch.cuda.current_stream(model.device)
@@ -618,11 +649,13 @@ class TrainStep(object):
             gX = eg.bwd[i].t_sized(Xin, S if first else 1, g_mean, g_var, need_gX=not first, phases=3 if first else 1)
             if not first:
                 g_mean, g_var = eg._sample_backward(i, gX, zs)
-        self._chain(0, wsize)
+        self._chain(0, wsize, with_elbo=sharded)
         # parameter-only remainder of the upper layers, each followed by its own chain
         for i in range(1, nl):
             eg.bwd[i].t_sized_rest()
             self._chain(i, wsize)
+        if sharded:
+            main.wait_event(self._elbo_ready)      # the returned scalar is complete in main-stream order
         return elbo
 
     def finish(self):

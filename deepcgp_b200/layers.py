@@ -153,6 +153,8 @@ class _PatchGPLayer(Layer):
         self._ready_fwd = None  # ... and the earlier point from which the forward operands are complete (set by prepare())
         self._ev_fwd = None
         self._pending = None    # set by grad.TrainStep: finishes this layer's pipelined update + prepare() (lazy, see there)
+        self._fresh = False     # prepare() for the CURRENT parameters is already queued (its completion event is _ready)
+        self._prep_done = None  # event recorded after the most recent prepare(), on whichever stream it ran
         self.algo = None
         if q_sqrt is None:
             if not self.white:                                              # layers.py:154-158 / DS/layers.py:168-174
@@ -184,6 +186,11 @@ class _PatchGPLayer(Layer):
         """Minibatch-independent work of the step (Kuu, Cholesky, L^-1, stacked operand W, KL)."""
         d = self._desc()
         dev = self.device
+        # Two prepares of one layer share the Kuu / factor / operand buffers: whatever streams they are queued on, the
+        # later one starts only after the earlier one has drained (TrainStep queues prepares on per-layer side streams).
+        cur = torch.cuda.current_stream(dev)
+        if self._prep_done is not None:
+            cur.wait_event(self._prep_done)
         nprep = _lib.lib.dcgp_prepare_bytes(d)
         if self._prep is None or self._prep.numel() < nprep:
             self._prep = torch.empty(nprep, dtype=torch.uint8, device=dev)
@@ -199,6 +206,8 @@ class _PatchGPLayer(Layer):
                                                   _lib.ptr(self._kl), _lib.ptr(ws), ws.numel(), _lib.ptr(self._info),
                                                   self._ev_fwd.cuda_event, _lib.stream()))
         self._ready_fwd = self._ev_fwd          # recorded inside the call, once the forward operands were queued
+        self._prep_done = torch.cuda.Event()
+        self._prep_done.record(cur)
         if check:
             _lib.raise_if_not_pd(self._info)
 

@@ -11,12 +11,21 @@ class MultiClass(object):
         self.num_classes = int(num_classes)
         self.epsilon = float(epsilon)
 
+    def _labels(self, Y, device):
+        """Labels as int32 on the device.  Host-side labels are range-checked here (tf.one_hot would silently produce an
+        all-zero row); labels already on the device are clamped by the kernels instead of being read back."""
+        if not (isinstance(Y, torch.Tensor) and Y.is_cuda):
+            Yh = torch.as_tensor(Y).reshape(-1)
+            if Yh.numel() and (int(Yh.min()) < 0 or int(Yh.max()) >= self.num_classes):
+                raise ValueError("MultiClass: labels must lie in [0, %d)" % self.num_classes)
+        return torch.as_tensor(Y, device=device).reshape(-1).to(torch.int32).contiguous()
+
     def variational_expectations(self, Fmu, Fvar, Y, S=1, out_sum=None):
         """Fmu, Fvar [S*N, K] float32; Y [N] integer labels -> [S*N] float64 (and the device-side sum)."""
         Fmu, Fvar = _lib.f32(Fmu), _lib.f32(Fvar, Fmu.device)
         SN, K = Fmu.shape
         N = SN // S
-        Y = torch.as_tensor(Y, device=Fmu.device).reshape(-1).to(torch.int32).contiguous()
+        Y = self._labels(Y, Fmu.device)
         assert Y.numel() == N and K == self.num_classes
         ve = torch.empty((SN,), dtype=torch.float64, device=Fmu.device)
         total = out_sum if out_sum is not None else torch.empty(1, dtype=torch.float64, device=Fmu.device)
@@ -34,7 +43,7 @@ class MultiClass(object):
         pvar = torch.empty((SN, K), dtype=torch.float64, device=dev)
         logd = None
         if Y is not None:
-            Y = torch.as_tensor(Y, device=dev).reshape(-1).to(torch.int32).contiguous()
+            Y = self._labels(Y, dev)
             assert Y.numel() == N
             logd = torch.empty((SN,), dtype=torch.float64, device=dev)
         _lib.check(_lib.lib.dcgp_multiclass_predict(_lib.ptr(Fmu), _lib.ptr(Fvar), _lib.ptr(Y), S, N, K, self.epsilon,

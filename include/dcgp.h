@@ -67,6 +67,17 @@ long long dcgp_launch_count(void);
  * returns the duration in milliseconds (-1 if none was recorded). */
 void dcgp_set_kernel_timing(int on);
 double dcgp_kernel_ms(int which);
+/* Tensor-pipe flops that launch really issued (split products x the k-blocks not skipped as structurally zero), counted by the
+ * launcher: the "executed" figure next to the algorithmic one in bench.py's roofline. */
+double dcgp_kernel_tensor_flops(int which);
+/* Precision of the three big T-sized GEMM families on the tensor-core path.  Every operand is held as two fp16 planes
+ * x = hi + lo (22 bits); a GEMM issues 3 products per k-step (Al*Bh + Ah*Bl + Ah*Bh: fp32-class), 2 (Al*Bh + Ah*Bh) or 1
+ * (Ah*Bh: fp16 operands, fp32 accumulation).  cond = second stage of the forward conditional (G_r = C_r^T a, which only feeds
+ * a sum of squares; the first stage a = Lm^-1 k, where cancellation happens, always uses 3), dk / dq = the two large
+ * backward GEMMs (conditionals.py:31-65 differentiated).  0 leaves a value unchanged.  Defaults: env DCGP_PROD_COND /
+ * DCGP_PROD_DK / DCGP_PROD_DQ, else the library's built-in choice (dcgp_get_products reports the values in force). */
+void dcgp_set_products(int cond, int dk, int dq);
+void dcgp_get_products(int* cond_host, int* dk_host, int* dq_host);
 
 /* views.py:56-68 FullView._patch_count/_patch_length/_out_image_size */
 int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH_host, int* OW_host, int* P_host, int* L_host);

@@ -121,8 +121,9 @@ def robustmax_varexp(Fmu, Fvar, Y, num_classes=10, epsilon=1e-3):
     return p * math.log(1.0 - epsilon) + (1.0 - p) * math.log(epsilon / (num_classes - 1.0))
 
 
-def dgp_elbo(layers, X, Y, zs, num_data, S, jitter=JITTER, n_global=None):
-    """ELBO (DS/dgp.py:92-98) as a differentiable torch scalar; layers from to_torch_layers()."""
+def dgp_elbo(layers, X, Y, zs, num_data, S, jitter=JITTER, n_global=None, keep=None):
+    """ELBO (DS/dgp.py:92-98) as a differentiable torch scalar; layers from to_torch_layers().
+    keep: optional list that receives (mean, var) [S,N,D] numpy arrays of every layer (DS/dgp.py:61-76 Fmeans, Fvars)."""
     X = torch.as_tensor(X, dtype=torch.float64)
     N = X.shape[0]
     F = X[None].repeat(S, 1, 1)
@@ -130,6 +131,8 @@ def dgp_elbo(layers, X, Y, zs, num_data, S, jitter=JITTER, n_global=None):
         mean, var = layer_forward(F.reshape(S * N, -1), lay, jitter)
         D = mean.shape[1]
         mean, var = mean.reshape(S, N, D), var.reshape(S, N, D)
+        if keep is not None:
+            keep.append((mean.detach().numpy().copy(), var.detach().numpy().copy()))
         F = mean + torch.as_tensor(z, dtype=torch.float64) * torch.sqrt(var + jitter)
     K = mean.shape[2]
     ve = robustmax_varexp(mean.reshape(S * N, K), var.reshape(S * N, K), np.tile(np.asarray(Y).reshape(-1), S), K)
@@ -138,10 +141,11 @@ def dgp_elbo(layers, X, Y, zs, num_data, S, jitter=JITTER, n_global=None):
     return Lsum * (float(num_data) / float(n_global or N)) - KL
 
 
-def elbo_and_grads(layers_np, X, Y, zs, num_data, S, jitter=JITTER):
-    """Returns (elbo, [ {param: dELBO/dparam (numpy)} per layer ]); q_sqrt gradients are lower-triangular."""
+def elbo_and_grads(layers_np, X, Y, zs, num_data, S, jitter=JITTER, keep=None):
+    """Returns (elbo, [ {param: dELBO/dparam (numpy)} per layer ]); q_sqrt gradients are lower-triangular.
+    keep: see dgp_elbo."""
     layers = to_torch_layers(layers_np)
-    elbo = dgp_elbo(layers, X, Y, zs, num_data, S, jitter)
+    elbo = dgp_elbo(layers, X, Y, zs, num_data, S, jitter, keep=keep)
     elbo.backward()
     grads = []
     for lay in layers:
