@@ -55,6 +55,8 @@ SIGNATURES = {
     "dcgp_prepare_workspace_bytes": (_sz, [_pd]),
     "dcgp_prepare_workspace_layout": (_i, [_pd, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     "dcgp_prepare_layout": (_i, [_pd, C.POINTER(_sz), C.POINTER(_i)]),
+    "dcgp_prepare_layout2": (_i, [_pd, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
+    "dcgp_prepare_workspace_layout2": (_i, [_pd, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     "dcgp_layer_prepare": (_i, [_pd, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "dcgp_layer_prepare_ev": (_i, [_pd, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "dcgp_apply_workspace_bytes": (_sz, [_pd, _i, _i]),

@@ -379,9 +379,11 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
     Lp = Kp;
     Lpinv = w.Lpinv;
   }
-  const int chained = (algo == DCGP_ALGO_TC && d->kind == DCGP_LAYER_CONV && tc_forward_chained()) ? 1 : 0;
-  if (chained) {
-    // The chained forward needs only Lm^-1, C_r^T and alpha: Kuu^-1 and beta (backward operands) wait behind the event.
+  if (algo == DCGP_ALGO_TC) {
+    // Forward operands first; the caller's event marks the point from which dcgp_layer_apply may run -- the KL (which joins
+    // the prior chain) and the backward operands follow on the same stream, off the forward's critical path.
+    // chained (default): a = Lm^-1 k, then G_r = C_r^T a: needs Lm^-1, C_r^T and alpha only.
+    const int chained = tc_forward_chained() ? 1 : 0;
     DCGP_TRY(factor_only(w, info, st));
     const double* alpha = q_mu;          // whitened: mean = a^T q_mu
     if (!d->white) {                     // alpha = Lm^-1 q_mu
@@ -393,12 +395,20 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
       DCGP_TRY(gemm_f64(g, st));
       alpha = w.alpha;
     }
-    DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, nullptr, 0, d->white ? 1 : 0, nullptr, w.Mq, q_sqrt, w.beta, w.sc + 1,
-                               nullptr, 1, 1, alpha, st));
-    DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
-    if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
-    DCGP_TRY(g_and_beta(w, d->white, q_mu, &gi, st));
-    if (d->white) {   // Q_0 = Kuu^-1 is needed by the backward operands even when G = Lm^-1
+    if (chained) {
+      DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, nullptr, 0, d->white ? 1 : 0, nullptr, w.Mq, q_sqrt, w.beta, w.sc + 1,
+                                 nullptr, 1, 1, alpha, st));
+      DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+      if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
+      DCGP_TRY(g_and_beta(w, d->white, q_mu, &gi, st));
+    } else {                             // dense single-stack forward (diagnostic): W_r = L_r^T G, beta
+      DCGP_TRY(g_and_beta(w, d->white, q_mu, &gi, st));
+      DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, nullptr, w.Mq, q_sqrt, w.beta, w.sc + 1,
+                                 nullptr, 1, 0, nullptr, st));
+      DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+      if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
+    }
+    if (d->white) {   // Kuu^-1 is read by the host's chain rule even when G = Lm^-1
       GemmF64 g{};
       g.m = g.n = g.k = M;
       g.A = w.Linv; g.lda = w.Mq; g.transA = 1; g.lowerA = 1;
@@ -408,30 +418,10 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
     }
     if (own_prior) cudaStreamWaitEvent(st, ax->join, 0);
     DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, 2, 1, alpha, st));
+                               w.beta, w.sc + 1, w.Kinv, 2, chained, alpha, st));
     return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
   }
   DCGP_TRY(factor_and_G(w, d->white, q_mu, info, &gi, st));
-  if (algo == DCGP_ALGO_TC) {
-    if (d->white) {   // Q_0 = Kuu^-1 is needed by the backward operands even when G = Lm^-1
-      GemmF64 g{};
-      g.m = g.n = g.k = M;
-      g.A = w.Linv; g.lda = w.Mq; g.transA = 1; g.lowerA = 1;
-      g.B = w.Linv; g.ldb = w.Mq; g.lowerB = 1;
-      g.C = w.Kinv; g.ldc = M; g.alpha = 1.0; g.batch = 1;
-      DCGP_TRY(gemm_f64(g, st));
-    }
-    // forward operands first; the caller's event marks the point from which dcgp_layer_apply may run -- the KL (which
-    // joins the prior chain) and the backward operands follow on the same stream, off the forward's critical path
-    DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, 1, 0, nullptr, st));
-    DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
-    if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
-    if (own_prior) cudaStreamWaitEvent(st, ax->join, 0);
-    DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, d->white ? nullptr : Lpinv, w.Mq, q_sqrt,
-                               w.beta, w.sc + 1, w.Kinv, 2, 0, nullptr, st));
-    return kl_terms(w, d->white, Lp, M, Lpinv, w.Mq, q_mu, q_sqrt, kl, st, /*have_trace=*/!d->white);
-  }
   if (own_prior) cudaStreamWaitEvent(st, ax->join, 0);
   if (own_prior) {   // the fp64 path needs w.Wr for W_r first: move the prior factor out of the way
     cudaMemcpyAsync(w.Kinv == gi.G ? w.tmpK : w.Kinv, Kp, (size_t)M * M * sizeof(double), cudaMemcpyDeviceToDevice, st);
@@ -458,6 +448,25 @@ int dcgp_prepare_workspace_layout(const dcgp_layer_desc* d, size_t* off_kinv, si
   if (off_linv) *off_linv = (size_t)((char*)w.Linv - fake);
   if (off_lpinv) *off_lpinv = (size_t)((char*)w.Lpinv - fake);
   if (ld_inv) *ld_inv = w.Mq;
+  return DCGP_OK;
+}
+
+int dcgp_prepare_workspace_layout2(const dcgp_layer_desc* d, size_t* off_kinv, size_t* off_linv, size_t* off_lpinv, size_t* off_lm,
+                                   int* ld_inv) {
+  if (check_desc(d)) return DCGP_ERR_ARG;
+  char* const fake = (char*)(uintptr_t)(1u << 20);
+  F64Work w = carve_f64(d->M, d->R, fake);
+  if (off_lm) *off_lm = (size_t)((char*)w.Kuu - fake);    // Kuu is factored in place: its lower triangle is Lm (ld M)
+  return dcgp_prepare_workspace_layout(d, off_kinv, off_linv, off_lpinv, ld_inv);
+}
+
+int dcgp_prepare_layout2(const dcgp_layer_desc* d, size_t* off_c32, size_t* off_s32, int* ld) {
+  if (check_desc(d)) return DCGP_ERR_ARG;
+  char* const fake = (char*)(uintptr_t)(1u << 20);
+  Prep p = carve_prep(d, fake);
+  if (off_c32) *off_c32 = (size_t)((char*)p.tc.Br32 - fake);
+  if (off_s32) *off_s32 = (size_t)((char*)p.tc.Qr32 - fake);
+  if (ld) *ld = p.Mp;
   return DCGP_OK;
 }
 

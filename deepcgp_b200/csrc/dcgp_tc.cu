@@ -246,6 +246,12 @@ __device__ __forceinline__ bool tile_descending(const TcParams& p, int item) {
   return item % per != per - 1;
 }
 template <int MODE, int BN>
+__device__ __forceinline__ bool mean_item(const TcParams& p, int item) {   // MODE_COND: the item that carries the mean rows
+  if (MODE != MODE_COND) return false;
+  const int per = p.R + 2 - p.blk_first;
+  return item % per == per - 1;
+}
+template <int MODE, int BN>
 __device__ __forceinline__ void kb_cols(const TcParams& p, bool desc, int jt, int kb, int& col_off, int& n) {
   col_off = 0; n = BN;
   if (MODE == MODE_A) { col_off = max(0, kb * kBK - jt * BN); n = BN - col_off; }
@@ -301,30 +307,41 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int njt = tiles_in_item<MODE, BN>(p, item);
         const bool desc = tile_descending<MODE, BN>(p, item);
+        // MODE_COND mean rows (alpha^T a): always the full 22-bit product.  With fewer than four plane slots per stage the
+        // k-range is walked three times with single planes in the hi slots: (A_lo, B_hi), (A_hi, B_lo), (A_hi, B_hi).
+        const bool mean3 = mean_item<MODE, BN>(p, item) && p.nprod < 3;
         for (int jt = 0; jt < njt; ++jt) {
           int arow, brow, kb0, kb1;
           tile_rows<MODE, BN>(p, item, jt, arow, brow);
           item_krange<MODE, BN>(p, item, jt, kb0, kb1);
-          for (int i = 0; i < kb1 - kb0; ++i) {
-            const int kb = desc ? kb1 - 1 - i : kb0 + i;
-            int col_off, n;
-            kb_cols<MODE, BN>(p, desc, jt, kb, col_off, n);
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * stage_bytes;
-            uint8_t* sb = st + a_planes * Cfg::kStageA;
-            mbar_expect_tx(&full_bar[stage], a_planes * Cfg::kStageA + b_planes * n * (kBK * 2));
-            tma_load_2d(st, &tmA_hi, &full_bar[stage], kb * kBK, arow);
-            if (a_planes == 2) tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, arow);
-            if (n == BN) {
-              tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kBK, brow);
-              if (b_planes == 2) tma_load_2d(sb + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb * kBK, brow);
-            } else {                                   // partial block: 64-row boxes of the non-zero rows only
-              for (int c = col_off; c < col_off + n; c += 64) {
-                tma_load_2d(sb + c * (kBK * 2), &tmB64_hi, &full_bar[stage], kb * kBK, brow + c);
-                if (b_planes == 2) tma_load_2d(sb + Cfg::kStageB + c * (kBK * 2), &tmB64_lo, &full_bar[stage], kb * kBK, brow + c);
+          for (int pass = 0; pass < (mean3 ? 3 : 1); ++pass) {
+            for (int i = 0; i < kb1 - kb0; ++i) {
+              const int kb = desc ? kb1 - 1 - i : kb0 + i;
+              int col_off, n;
+              kb_cols<MODE, BN>(p, desc, jt, kb, col_off, n);
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* st = smem + stage * stage_bytes;
+              uint8_t* sb = st + a_planes * Cfg::kStageA;
+              if (mean3) {
+                mbar_expect_tx(&full_bar[stage], Cfg::kStageA + Cfg::kStageB);
+                tma_load_2d(st, pass == 0 ? &tmA_lo : &tmA_hi, &full_bar[stage], kb * kBK, arow);
+                tma_load_2d(sb, pass == 1 ? &tmB_lo : &tmB_hi, &full_bar[stage], kb * kBK, brow);
+              } else {
+                mbar_expect_tx(&full_bar[stage], a_planes * Cfg::kStageA + b_planes * n * (kBK * 2));
+                tma_load_2d(st, &tmA_hi, &full_bar[stage], kb * kBK, arow);
+                if (a_planes == 2) tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, arow);
+                if (n == BN) {
+                  tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kBK, brow);
+                  if (b_planes == 2) tma_load_2d(sb + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb * kBK, brow);
+                } else {                                   // partial block: 64-row boxes of the non-zero rows only
+                  for (int c = col_off; c < col_off + n; c += 64) {
+                    tma_load_2d(sb + c * (kBK * 2), &tmB64_hi, &full_bar[stage], kb * kBK, brow + c);
+                    if (b_planes == 2) tma_load_2d(sb + Cfg::kStageB + c * (kBK * 2), &tmB64_lo, &full_bar[stage], kb * kBK, brow + c);
+                  }
+                }
               }
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
-            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -338,6 +355,8 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int njt = tiles_in_item<MODE, BN>(p, item);
         const bool desc = tile_descending<MODE, BN>(p, item);
+        const bool mean3 = mean_item<MODE, BN>(p, item) && p.nprod < 3;
+        const bool two_a = !mean3 && a_planes == 2, two_b = !mean3 && b_planes == 2;
         for (int jt = 0; jt < njt; ++jt, ++tile) {
           const uint32_t buf = tile & 1, use = tile >> 1;
           mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);     // epilogue has drained this accumulator
@@ -345,31 +364,33 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           int kb0, kb1;
           item_krange<MODE, BN>(p, item, jt, kb0, kb1);
           uint32_t acc = 0;                               // the first MMA of the tile overwrites the accumulator
-          for (int i = 0; i < kb1 - kb0; ++i) {
-            const int kb = desc ? kb1 - 1 - i : kb0 + i;
-            int col_off, n;
-            kb_cols<MODE, BN>(p, desc, jt, kb, col_off, n);
-            const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
-            const uint32_t d_tmem = tmem_base + buf * BN + col_off;
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
-            const uint32_t a_lo = a_hi + Cfg::kStageA;
-            const uint32_t b_hi = a_hi + a_planes * Cfg::kStageA + col_off * (kBK * 2);
-            const uint32_t b_lo = b_hi + Cfg::kStageB;
-            const uint64_t dah = make_sw128_desc(a_hi), dal = make_sw128_desc(a_lo);
-            const uint64_t dbh = make_sw128_desc(b_hi), dbl = make_sw128_desc(b_lo);
+          for (int pass = 0; pass < (mean3 ? 3 : 1); ++pass) {
+            for (int i = 0; i < kb1 - kb0; ++i) {
+              const int kb = desc ? kb1 - 1 - i : kb0 + i;
+              int col_off, n;
+              kb_cols<MODE, BN>(p, desc, jt, kb, col_off, n);
+              const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
+              const uint32_t d_tmem = tmem_base + buf * BN + col_off;
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
+              const uint32_t a_lo = a_hi + Cfg::kStageA;
+              const uint32_t b_hi = a_hi + a_planes * Cfg::kStageA + col_off * (kBK * 2);
+              const uint32_t b_lo = b_hi + Cfg::kStageB;
+              const uint64_t dah = make_sw128_desc(a_hi), dal = make_sw128_desc(a_lo);
+              const uint64_t dbh = make_sw128_desc(b_hi), dbl = make_sw128_desc(b_lo);
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // advance 32 bytes inside the swizzle atom
-              // small cross terms first, dominant term last
-              if (a_planes == 2) { umma_f16(d_tmem, dal + koff, dbh + koff, idesc, acc); acc = 1; }
-              if (b_planes == 2) { umma_f16(d_tmem, dah + koff, dbl + koff, idesc, acc); acc = 1; }
-              umma_f16(d_tmem, dah + koff, dbh + koff, idesc, acc);
-              acc = 1;
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);   // advance 32 bytes inside the swizzle atom
+                // small cross terms first, dominant term last
+                if (two_a) { umma_f16(d_tmem, dal + koff, dbh + koff, idesc, acc); acc = 1; }
+                if (two_b) { umma_f16(d_tmem, dah + koff, dbl + koff, idesc, acc); acc = 1; }
+                umma_f16(d_tmem, dah + koff, dbh + koff, idesc, acc);
+                acc = 1;
+              }
+              umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&empty_bar[stage]);                 // smem slot reusable once these MMAs retire
-            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
           umma_commit(&tmem_full[buf]);                     // accumulator complete -> epilogue
         }
@@ -679,9 +700,28 @@ bool tc_forward_chained() {
 //   stage 1 (MODE_A):   a = K Lm^-T         -> acc[:, 0] = |a|^2, planes of a        (Lm^-1 lower triangular: 3/4 of the k-blocks)
 //   stage 2 (MODE_COND) G_r = a C_r, mean   -> acc[:, r] = |G_r|^2, mean             (C_r^T upper triangular: 3/4 of the k-blocks)
 // |a|^2 <= k(x, x) (the conditional variance is non-negative), so sqrt(a_bound) bounds every entry of a: data-independent scale.
+// scal2 = scale pair for bound * max(1e-30, max_p |w_p|)   (image-level rows: |a|^2 <= Kdiag <= variance max|w|^2)
+__global__ void set_scale_w_kernel(float bound, const double* __restrict__ w, int P, float* __restrict__ scal2) {
+  __shared__ float sh[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) m = fmaxf(m, (float)fabs(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, sh[i]);
+    int e = 0;
+    frexpf(bound * fmaxf(m, 1e-30f), &e);
+    const float s = ldexpf(1.f, 14 - e);
+    scal2[0] = s;
+    scal2[1] = 1.f / s;
+  }
+}
+
 template <int BN>
-static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc,
-                               float* mean, cudaStream_t st) {
+static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, const double* pw,
+                               int P, float* acc, float* mean, cudaStream_t st) {
   CUtensorMap tmKh, tmKl, tmAh, tmAl, tmBh, tmBl, tmB64h, tmB64l;
   int rc;
   if ((rc = make_tmap_f16(&tmKh, w.Kh, w.Tpad, Mp, kBM))) return rc;
@@ -692,7 +732,8 @@ static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, i
   if ((rc = make_tmap_f16(&tmBl, prep.Wl, w_rows(Mp, R), Mp, BN))) return rc;
   if ((rc = make_tmap_f16(&tmB64h, prep.Wh, w_rows(Mp, R), Mp, 64))) return rc;
   if ((rc = make_tmap_f16(&tmB64l, prep.Wl, w_rows(Mp, R), Mp, 64))) return rc;
-  set_scale_kernel<<<1, 1, 0, st>>>(sqrtf(a_bound), w.ascal);
+  if (pw) set_scale_w_kernel<<<1, 256, 0, st>>>(sqrtf(a_bound), pw, P, w.ascal);
+  else set_scale_kernel<<<1, 1, 0, st>>>(sqrtf(a_bound), w.ascal);
   if ((rc = check_launch("set_scale"))) return rc;
   ScopedTimer timer(0, st);
   const int nprod2 = tc_products().cond;
@@ -700,7 +741,7 @@ static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, i
     const int nb = Mp / kBK;                                   // 64-blocks per side
     const double tri_blocks = 0.5 * nb * (nb + 1);             // (k-block, 64-column block) pairs that are not structurally zero
     const double per_blk = 2.0 * (double)w.Tpad * kBK * kBK;   // one 64 x 64 block pair over all patch columns
-    timer.flops(3 * per_blk * tri_blocks + nprod2 * (per_blk * tri_blocks * R + 2.0 * (double)w.Tpad * BN * Mp));
+    timer.flops(3 * per_blk * tri_blocks + nprod2 * per_blk * tri_blocks * R + 3 * 2.0 * (double)w.Tpad * BN * Mp);
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -717,12 +758,12 @@ static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, i
 }
 
 int tc_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc, float* mean,
-                    cudaStream_t st) {
+                    cudaStream_t st, const double* patch_weights, int P) {
   if (R > 64) { set_error("tc_cond: R > 64 unsupported"); return DCGP_ERR_ARG; }
   if (!w.Ah) { set_error("tc_cond_chained: no workspace for the a planes"); return DCGP_ERR_ARG; }
-  if (Mp % 256 == 0) return launch_cond_chained<256>(prep, w, T, Mp, R, a_bound, acc, mean, st);
-  if (Mp % 128 == 0) return launch_cond_chained<128>(prep, w, T, Mp, R, a_bound, acc, mean, st);
-  return launch_cond_chained<64>(prep, w, T, Mp, R, a_bound, acc, mean, st);
+  if (Mp % 256 == 0) return launch_cond_chained<256>(prep, w, T, Mp, R, a_bound, patch_weights, P, acc, mean, st);
+  if (Mp % 128 == 0) return launch_cond_chained<128>(prep, w, T, Mp, R, a_bound, patch_weights, P, acc, mean, st);
+  return launch_cond_chained<64>(prep, w, T, Mp, R, a_bound, patch_weights, P, acc, mean, st);
 }
 
 // Batched C[b] = A[b] * B[b]^T on split-fp16 planes (both K-major, row-stacked batches); rows/K padded by the caller.
@@ -920,9 +961,10 @@ __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, cons
   }
 }
 
-// QP planes [R*Mp + 256, Mp]: row (r-1)*Mp + i = 2 (Q_r[i,:] - Q_0[i,:]), Q_0 = Kuu^-1 (float64), Q_r float32 (symmetric);
-// the remaining rows are zero.  Scale from the bound 4 * max(|Q_r|, |Q_0|); thread 0 publishes {scale, 1/scale}.
-// Also writes beta32 [Mp, 64] for the mean path of the distance-gradient kernel.
+// SP planes [R*Mp + 256, Mp]: row (r-1)*Mp + i = 2 (S_r[i,:] - I[i,:]), S_r = C_r C_r^T float32 (symmetric; Kinv == nullptr) --
+// or, in the Q-form, 2 (Q_r - Q_0) with Q_0 = Kinv (float64); the remaining rows are zero.  Scale from the bound
+// 4 * max(|S_r|, 1); thread 0 publishes {scale, 1/scale}.  Also writes the planes of alpha [Mp, 64] (`beta` argument) for the
+// mean tile of the da GEMM.
 __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float* __restrict__ Qr, const double* __restrict__ beta,
                                    int M, int Mp, int R, const float* __restrict__ mxq, float* __restrict__ scal2,
                                    __half* __restrict__ QPh, __half* __restrict__ QPl, float* __restrict__ beta32,
@@ -945,7 +987,7 @@ __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float*
     double v = 0.0;
     if (row < (long long)R * Mp) {
       const int r = (int)(row / Mp), i = (int)(row % Mp);
-      if (i < M && j < M) v = 2.0 * sc * ((double)Qr[((long long)r * Mp + i) * Mp + j] - Kinv[(long long)i * M + j]);
+      if (i < M && j < M) v = 2.0 * sc * ((double)Qr[((long long)r * Mp + i) * Mp + j] - (Kinv ? Kinv[(long long)i * M + j] : (i == j ? 1.0 : 0.0)));
     }
     const __half hi = __float2half_rn((float)v);
     QPh[e] = hi;
@@ -1066,6 +1108,8 @@ void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf) {
   t.ZTl = c.take((size_t)t.LpT * Mp * 2);
   t.BTh = c.take((size_t)Mp * 64 * 2);
   t.BTl = c.take((size_t)Mp * 64 * 2);
+  t.LTh = c.take(((size_t)Mp + 256) * Mp * 2);
+  t.LTl = c.take(((size_t)Mp + 256) * Mp * 2);
   t.Wmh = t.Wml = nullptr;
   t.bytes = align_up(c.off, 1024);
 }
@@ -1094,6 +1138,18 @@ __global__ void qsqrt_t_f32_kernel(const double* __restrict__ q_sqrt, int M, int
     out[e] = (i < M && j < M && i >= j) ? (float)q_sqrt[((long long)r * M + i) * M + j] : 0.f;
   }
 }
+
+// out[(r*Mp + i)*Mp + k] = L_r[i, k] (i >= k), 0 elsewhere: C_r for the whitened parameterisation
+__global__ void qsqrt_f32_kernel(const double* __restrict__ q_sqrt, int M, int Mp, int R, float* __restrict__ out) {
+  const long long total = (long long)R * Mp * Mp;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % Mp);
+    const long long q = e / Mp;
+    const int i = (int)(q % Mp), r = (int)(q / Mp);
+    out[e] = (i < M && k < M && i >= k) ? (float)q_sqrt[((long long)r * M + i) * M + k] : 0.f;
+  }
+}
+__global__ void set_max_kernel(float* __restrict__ mx, float v) { mx[0] = fmaxf(mx[0], v); }
 
 // Tensor-core build of the R-batched M-only products (the O(R M^3) part of the step's minibatch-independent work):
 //   W_r = L_r^T G            (G = Kuu^-1 symmetric, or Lm^-1 when whitened)                -> fp32, then the W planes
@@ -1152,12 +1208,7 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
   }
   if (!(parts & 2)) return DCGP_OK;
   // ---- part 2: KL trace and the backward operands (not needed by the forward conditional)
-  if (chained) {   // the G planes (A operand of B_r = G L_r below) were not needed by part 1
-    if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc;
-    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 3, 1, t.scal);
-    if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
-    cudaMemsetAsync(t.mx + 4, 0, sizeof(float), st);
-  }
+  cudaMemsetAsync(t.mx + 3, 0, 2 * sizeof(float), st);   // slots 3 (Lm^-1 planes below) and 4 (prior's Lp^-1)
   if (Lpinv) {
     if ((rc = maxabs_f64(Lpinv, M, M, ldp, 0, t.mx + 4, st))) return rc;
     scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 4, 1, t.scal);
@@ -1174,17 +1225,30 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
     if ((rc = tc_gemm(h, st))) return rc;
   }
   if (!Kinv) return DCGP_OK;
-  // ---- backward operands: B_r = G L_r (= W_r^T), Q_r = B_r B_r^T, QB planes [Mp, Jp] = [2Q_0 | ... | 2Q_R | beta | 0]
+  // ---- backward operands, in the order of the forward (a = Lm^-1 k first):  C_r = Lm^-1 L_r (or L_r when whitened),
+  //      S_r = C_r C_r^T, SP planes [R*Mp + 256, Mp] = 2 (S_r - I), alpha planes, Lm^-T planes.  Br32 keeps C_r for the host's
+  //      M-only chain rule.
   {
-    TcGemm b1;
-    memset(&b1, 0, sizeof(b1));
-    b1.Ah = t.Gh; b1.Al = t.Gl; b1.a_rows_total = Mp; b1.a_batch_rows = 0;
-    b1.Bh = t.QTh; b1.Bl = t.QTl; b1.b_rows_total = (long long)R * Mp; b1.b_batch_rows = Mp;
-    b1.batch = R; b1.m = M; b1.n = M; b1.m_pad = Mp; b1.n_pad = Mp; b1.k_pad = Mp;
-    b1.a_scal = t.scal + 6; b1.b_scal = t.scal + 4;
-    b1.C = t.Br32; b1.c_batch_stride = (long long)Mp * Mp; b1.ldc = Mp;
-    if (M != Mp) cudaMemsetAsync(t.Br32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
-    if ((rc = tc_gemm(b1, st))) return rc;
+    if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 3, st))) return rc;      // (slot 3 was zeroed by part 1 / above)
+    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 3, 1, t.scal);
+    if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
+    cudaMemsetAsync((char*)t.LTh + (size_t)Mp * Mp * 2, 0, (size_t)256 * Mp * 2, st);
+    cudaMemsetAsync((char*)t.LTl + (size_t)Mp * Mp * 2, 0, (size_t)256 * Mp * 2, st);
+    if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 1, 1, 1, Mp, Mp, t.scal + 6, t.LTh, t.LTl, st))) return rc;
+    if (g_is_linv) {          // whitened: C_r = L_r
+      qsqrt_f32_kernel<<<num_sms() * 8, 256, 0, st>>>(q_sqrt, M, Mp, R, t.Br32);
+      if ((rc = check_launch("qsqrt_f32"))) return rc;
+    } else {
+      TcGemm b1;
+      memset(&b1, 0, sizeof(b1));
+      b1.Ah = t.Gh; b1.Al = t.Gl; b1.a_rows_total = Mp; b1.a_batch_rows = 0;
+      b1.Bh = t.QTh; b1.Bl = t.QTl; b1.b_rows_total = (long long)R * Mp; b1.b_batch_rows = Mp;
+      b1.batch = R; b1.m = M; b1.n = M; b1.m_pad = Mp; b1.n_pad = Mp; b1.k_pad = Mp;
+      b1.a_scal = t.scal + 6; b1.b_scal = t.scal + 4;
+      b1.C = t.Br32; b1.c_batch_stride = (long long)Mp * Mp; b1.ldc = Mp;
+      if (M != Mp) cudaMemsetAsync(t.Br32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
+      if ((rc = tc_gemm(b1, st))) return rc;
+    }
     if ((rc = maxabs_f32(t.Br32, (long long)R * Mp * Mp, t.mx + 7, st))) return rc;
     scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 7, 1, t.scal);
     split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(t.Br32, (long long)R * Mp, Mp, (long long)R * Mp, t.scal + 14, (__half*)t.BRh,
@@ -1195,15 +1259,15 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
     b2.Bh = t.BRh; b2.Bl = t.BRl; b2.b_rows_total = (long long)R * Mp; b2.b_batch_rows = Mp;
     b2.batch = R; b2.m = M; b2.n = M; b2.m_pad = Mp; b2.n_pad = Mp; b2.k_pad = Mp;
     b2.a_scal = t.scal + 14; b2.b_scal = t.scal + 14;
-    b2.C = t.Qr32; b2.c_batch_stride = (long long)Mp * Mp; b2.ldc = Mp;     // Br32 keeps B_r for the M-only chain rule
+    b2.C = t.Qr32; b2.c_batch_stride = (long long)Mp * Mp; b2.ldc = Mp;     // S_r; Br32 keeps C_r for the M-only chain rule
     if (M != Mp) cudaMemsetAsync(t.Qr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
     if ((rc = tc_gemm(b2, st))) return rc;
     if ((rc = maxabs_f32(t.Qr32, (long long)R * Mp * Mp, t.mx + 5, st))) return rc;
-    if ((rc = maxabs_f64(Kinv, M, M, M, 0, t.mx + 5, st))) return rc;
-    if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 6, st))) return rc;
-    pack_qp_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Kinv, t.Qr32, beta, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl,
+    set_max_kernel<<<1, 1, 0, st>>>(t.mx + 5, 1.f);                         // the identity in S_r - I
+    if ((rc = maxabs_f64(alpha, M, R, R, 0, t.mx + 6, st))) return rc;
+    pack_qp_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(nullptr, t.Qr32, alpha, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl,
                                                       t.beta32, t.scal + 16, (__half*)t.BTh, (__half*)t.BTl);
-    if ((rc = check_launch("tc_build_backward_operands", 3))) return rc;
+    if ((rc = check_launch("tc_build_backward_operands", 4))) return rc;
   }
   return DCGP_OK;
 }
@@ -1563,6 +1627,9 @@ void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_
     a.kz.Kh = c.take(a.kz.Tpad * Mp * 2);
     a.kz.Kl = c.take(a.kz.Tpad * Mp * 2);
     a.kz.kscal = (float*)c.take(8 * 4);
+    a.kz.Ah = c.take(a.kz.Tpad * Mp * 2);          // planes of a = Lm^-1 kzx (image-level rows)
+    a.kz.Al = c.take(a.kz.Tpad * Mp * 2);
+    a.kz.ascal = (float*)c.take(8 * 4);
   }
   a.bytes = align_up(c.off, 1024);
 }
@@ -1588,6 +1655,8 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
                                                                           patch_weights, a.kk.kscal, Kzx);
   if ((rc = check_launch("patch_mean_planes"))) return rc;
   if ((rc = tc_split_rows(Kzx, n_rows, Mp, a.kz, st))) return rc;
+  // |a|^2 = kzx^T Kuu^-1 kzx <= Kdiag <= variance max|w|^2
+  if (tc_forward_chained()) return tc_cond_chained(prep, a.kz, n_rows, Mp, R, variance, acc, mean_t, st, patch_weights, v.P);
   return tc_cond(prep, a.kz, n_rows, Mp, R, acc, mean_t, st);
 }
 

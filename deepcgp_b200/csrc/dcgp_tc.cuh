@@ -26,7 +26,8 @@ struct TcPrep {
   void *QBh, *QBl;   // [R*Mp + 256, Mp]  QP_r = 2 (Q_r - Q_0) stacked over r = 1..R (B operand of the dK GEMM), zero padded
   float* beta32;     // [Mp, 64]     beta[m, r] (fp32), zero padded
   void *ZTh, *ZTl;   // [LpT, Mp]    bf16 planes of (Z / lengthscale)^T * kXScale; row L = kXScale (ones row: DDZ[:, L] = row sums of dd)
-  void *BTh, *BTl;   // [Mp, 64]     fp16 planes of beta[m, r] (B operand of the mean-path tile of the dK GEMM)
+  void *BTh, *BTl;   // [Mp, 64]     fp16 planes of alpha[m, r] (B operand of the mean tile of the da GEMM)
+  void *LTh, *LTl;   // [Mp + 256, Mp] fp16 planes of Lm^-T (row m, column j: Lm^-1[j, m]; B operand of dK = da Lm^-1), zero padded
   size_t bytes;
 };
 void tc_carve_prep(TcPrep& t, int M, int Mp, int R, int L, void* buf);
@@ -52,7 +53,8 @@ void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf);
 int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStream_t st);
 int tc_cond(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float* acc, float* mean, cudaStream_t st);
 // chained form (prep.chained): a = K Lm^-T with |a|^2 -> acc[:, 0] and the a planes, then G_r = a C_r (upper-triangular operand)
-int tc_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc, float* mean, cudaStream_t st);
+int tc_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, int Mp, int R, float a_bound, float* acc, float* mean, cudaStream_t st,
+                    const double* patch_weights = nullptr, int P = 0);   // patch_weights: the bound on |a| is scaled by max|w| (image-level rows)
 bool tc_forward_chained();   // DCGP_FWD_CHAINED != 0 (default on)
 
 // Generic batched NT GEMM on split-fp16 planes: C[b][i,j] = sum_k A[b*a_batch_rows + i, k] * B[b*b_batch_rows + j, k].
@@ -105,7 +107,7 @@ struct TcBwdWork {
   float *gm, *s, *sT, *gmT32, *gknn, *scal, *dK32, *part2, *partb, *rowdot, *DDZ, *part4;
   double *DDX, *redpart;
   int n_redpart;
-  void *GTh, *GTl, *GMh, *GMl, *KTh, *KTl, *Dh, *Dl, *DTh, *DTl, *PTh, *PTl;   // D*, DT*, PT*: bf16 planes
+  void *GTh, *GTl, *GMh, *GMl, *KTh, *KTl, *DAh, *DAl, *Dh, *Dl, *DTh, *DTl, *PTh, *PTl;   // D*, DT*, PT*: bf16 planes; KT*: a^T
   size_t bytes;
 };
 void tc_carve_bwd(TcBwdWork& b, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, int P, void* buf);

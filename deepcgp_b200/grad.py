@@ -79,15 +79,6 @@ class LayerBackward(object):
             _lib.ptr(self.gw) if layer._kind == _lib.LAYER_SVGP_CONV else None, _lib.ptr(ws), ws.numel(), phases,
             _lib.stream()))
 
-    def m_only(self, kl_weight=1.0, hyp=None, static=None):
-        """Chain rule through the minibatch-independent operands; returns d ELBO / d{Z, variance, lengthscale, q_mu,
-        q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that summing over ranks counts the KL once.
-        `hyp` (optional): device tensor [variance, lengthscale] to use instead of the host floats -- keeps the whole chain
-        free of host values so that it can be captured in a CUDA graph (TrainStep)."""
-        if self.layer.white:
-            return self._m_only_autograd(kl_weight)
-        return self._m_only_closed_form(kl_weight, hyp, static)
-
     @staticmethod
     def _rbf_parts(Z, var, ls):
         Zs = Z / ls
@@ -107,30 +98,24 @@ class LayerBackward(object):
         gZ = -(Hs.sum(1, keepdim=True) * Z - Hs @ Z) / (ls * ls)
         return gvar, gls, gZ
 
-    def _forward_inverses(self):
-        """Views of Kuu^-1 [M,M] and Lp^-1 [M,M] inside the workspace of the layer's last dcgp_layer_prepare."""
-        import ctypes as C
-        layer, M = self.layer, self.M
-        if self._offs is None:
-            ok, ol, op, ld = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int()
-            _lib.check(_lib.lib.dcgp_prepare_workspace_layout(layer._desc(), C.byref(ok), C.byref(ol), C.byref(op), C.byref(ld)))
-            self._offs = (ok.value, ol.value, op.value, ld.value)
-        ok, ol, op, ld = self._offs
-        ws = layer._ws.get("prep", 0, layer.device)
-        Kinv = ws[ok:ok + M * M * 8].view(torch.float64).view(M, M)
-        Lpinv = ws[op:op + ld * ld * 8].view(torch.float64).view(ld, ld)[:M, :M]
-        return Kinv, Lpinv
-
-    def _forward_B(self):
-        """View of B_r = Kuu^-1 L_r (float32 [R, M, M], tensor-core product of this step's dcgp_layer_prepare)."""
+    def _views(self):
+        """Views of this step's float64 factors inside the workspace of the layer's last dcgp_layer_prepare -- Kuu^-1 [M,M],
+        Lm [M,M] (lower), Lm^-1 [M,M] (lower), the prior's Lp^-1 [M,M] -- and of the float32 tensor-core products it left in
+        the `prep` buffer: C_r = Lm^-1 L_r (L_r when whitened) and S_r = C_r C_r^T, each [R,M,M]."""
         import ctypes as C
         layer, M, R = self.layer, self.M, self.R
-        if getattr(self, "_boff", None) is None:
-            ob, ld = C.c_size_t(), C.c_int()
-            _lib.check(_lib.lib.dcgp_prepare_layout(layer._desc(), C.byref(ob), C.byref(ld)))
-            self._boff = (ob.value, ld.value)
-        ob, ld = self._boff
-        return layer._prep[ob:ob + R * ld * ld * 4].view(torch.float32).view(R, ld, ld)[:, :M, :M]
+        if self._offs is None:
+            ok, ol, op, olm, ld = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int()
+            _lib.check(_lib.lib.dcgp_prepare_workspace_layout2(layer._desc(), C.byref(ok), C.byref(ol), C.byref(op), C.byref(olm),
+                                                               C.byref(ld)))
+            oc, os_, ldb = C.c_size_t(), C.c_size_t(), C.c_int()
+            _lib.check(_lib.lib.dcgp_prepare_layout2(layer._desc(), C.byref(oc), C.byref(os_), C.byref(ldb)))
+            self._offs = (ok.value, ol.value, op.value, olm.value, ld.value, oc.value, os_.value, ldb.value)
+        ok, ol, op, olm, ld, oc, os_, ldb = self._offs
+        ws = layer._ws.get("prep", 0, layer.device)
+        f64 = lambda off, n: ws[off:off + n * n * 8].view(torch.float64).view(n, n)
+        f32 = lambda off: layer._prep[off:off + R * ldb * ldb * 4].view(torch.float32).view(R, ldb, ldb)[:, :M, :M]
+        return dict(Kinv=f64(ok, M), Li=f64(ol, ld)[:M, :M], Lpinv=f64(op, ld)[:M, :M], Lm=f64(olm, M), C=f32(oc), S=f32(os_))
 
     # The R-batched M^3 products of the chain rule: on the library's own tcgen05 GEMM (default), else through cuBLAS in shapes
     # it handles well (the [M,R*M] x [R*M,M] form of sum_r A_r B_r^T gets 32x32 tiles and 4 TFLOP/s: bmm + reduction instead)
@@ -173,12 +158,13 @@ class LayerBackward(object):
 
     @torch.no_grad()
     def m_only_static(self, kl_weight=1.0, hyp=None):
-        """The part of the (non-whitened) chain rule that depends only on the parameters and on this step's
-        dcgp_layer_prepare -- Kuu and its distance matrix, the KL gradient, the operand casts -- i.e. everything that can be
-        computed BEFORE the layer's dQ / dbeta exist.  TrainStep runs it on the layer's side stream during the forward
-        pass, which takes ~40 % of the chain off the serial tail of the step."""
+        """The part of the chain rule that depends only on the parameters and on this step's dcgp_layer_prepare -- Kuu and its
+        distance matrix, the KL gradient, the operand casts -- i.e. everything that can be computed BEFORE the layer's
+        dS / dalpha exist.  TrainStep runs it on the layer's side stream during the forward pass, which takes ~40 % of the
+        chain off the serial tail of the step."""
         layer = self.layer
         M, R = self.M, self.R
+        white = layer.white
         Z = layer.feature.Z.to(torch.float64)
         if hyp is None:
             var, ls = float(layer._base_kernel.variance), float(layer._base_kernel.lengthscales)
@@ -186,97 +172,84 @@ class LayerBackward(object):
             var, ls = hyp[0], hyp[1]
         q_mu, Lq = layer.q_mu, torch.tril(layer.q_sqrt)
         Kn, D = self._rbf_parts(Z, var, ls)
-        # Kuu^-1 and the prior's Lp^-1 were already formed (float64) by this step's dcgp_layer_prepare: re-use them
-        Kinv, Lpinv = self._forward_inverses()
+        vw = self._views()
+        Kinv, Lpinv, Li = vw["Kinv"], vw["Lpinv"], vw["Li"]
+        Lm = torch.tril(vw["Lm"])
         conv = isinstance(layer, ConvLayer)
         bt = self.BATCHED_DTYPE
-
-        bsum, left = self._bsum, self._left
-
-        # The R-batched M^3 products run in BATCHED_DTYPE (float32 by default: their inputs -- dQ from the split-fp16
-        # GEMMs, B_r from the forward -- carry 22-24 bits anyway, and cuBLAS float64 batched GEMMs reach only ~5 TFLOP/s
-        # here: 80 % of this chain at M=512, 90 % at M=1024); everything single-matrix stays float64.
+        # The R-batched M^3 products run in BATCHED_DTYPE (float32 by default: their inputs -- dS from the split-fp16 GEMMs,
+        # C_r / S_r from the forward -- carry 22-24 bits anyway); everything single-matrix stays float64.
         Lqb = Lq.to(bt)
-        Kinvb = Kinv.to(bt)
-        if layer._algo() == _lib.ALGO_TC:
-            Bb = self._forward_B().to(bt)                                # [R,M,M] = Kinv @ Lq, already formed this step
+        inv_diag = torch.diag_embed(1.0 / torch.diagonal(Lq, dim1=1, dim2=2))
+        gvar_p = gls_p = 0.0
+        GU_kl = None
+        if white:       # KL = 1/2 [ |q_mu|^2 - MR - sum log diag(L_r)^2 + sum |L_r|^2 ]
+            g_qmu_kl = -kl_weight * q_mu
+            gLq_kl = -kl_weight * (Lq - inv_diag)
         else:
-            Bb = self._left(Kinvb, Lqb).contiguous()
-        if conv:    # prior = Kuu at the initial Z (a constant) with the live hyper-parameters (layers.py:149-150)
-            Zp = layer.Z_prior.to(torch.float64)
-            Kpn, Dp = self._rbf_parts(Zp, var, ls)
-            Kpinv = Lpinv.T @ Lpinv
-            Cb = left(Kpinv.to(bt), Lqb)
+            if conv:    # prior = Kuu at the initial Z (a constant) with the live hyper-parameters (layers.py:149-150)
+                Zp = layer.Z_prior.to(torch.float64)
+                Kpn, Dp = self._rbf_parts(Zp, var, ls)
+                Kpinv = Lpinv.T @ Lpinv
+            else:
+                Kpinv = Kinv
+            Cb = self._left(Kpinv.to(bt), Lqb)
             a = Kpinv @ q_mu
-        else:
-            Kpinv, Cb = Kinv, Bb
-            a = Kinv @ q_mu
-        dKL_dKp = 0.5 * (-(a @ a.T) - bsum(Cb, Cb).to(torch.float64) + R * Kpinv)
-        g_qmu_kl = -kl_weight * a
-        gLq_kl = -kl_weight * (Cb.to(torch.float64) - torch.diag_embed(1.0 / torch.diagonal(Lq, dim1=1, dim2=2)))
-        if conv:
-            gvar_p, gls_p, _ = self._rbf_chain(-kl_weight * dKL_dKp, Kpn, Dp, Zp, var, ls, need_Z=False)
-            GU_kl = None
-        else:
-            GU_kl = -kl_weight * dKL_dKp
-            gvar_p = gls_p = 0.0
-        return dict(Z=Z, var=var, ls=ls, q_mu=q_mu, Kn=Kn, D=D, Kinv=Kinv, Kinvb=Kinvb, Bb=Bb, Lqb=Lqb,
-                    g_qmu_kl=g_qmu_kl, gLq_kl=gLq_kl, GU_kl=GU_kl, gvar_p=gvar_p, gls_p=gls_p)
+            dKL_dKp = 0.5 * (-(a @ a.T) - self._bsum(Cb, Cb).to(torch.float64) + R * Kpinv)
+            g_qmu_kl = -kl_weight * a
+            gLq_kl = -kl_weight * (Cb.to(torch.float64) - inv_diag)
+            if conv:
+                gvar_p, gls_p, _ = self._rbf_chain(-kl_weight * dKL_dKp, Kpn, Dp, Zp, var, ls, need_Z=False)
+            else:
+                GU_kl = -kl_weight * dKL_dKp
+        alpha = q_mu if white else Li @ q_mu
+        return dict(Z=Z, var=var, ls=ls, q_mu=q_mu, Kn=Kn, D=D, Li=Li, LiT=Li.T.contiguous(), LiTb=Li.T.to(bt).contiguous(), Lm=Lm,
+                    alpha=alpha, Cb=vw["C"].to(bt), Sb=vw["S"].to(bt), g_qmu_kl=g_qmu_kl, gLq_kl=gLq_kl, GU_kl=GU_kl, gvar_p=gvar_p,
+                    gls_p=gls_p)
 
     @torch.no_grad()
-    def _m_only_closed_form(self, kl_weight, hyp=None, static=None):
-        """Non-whitened case, written out as ~15 batched GEMMs (no autograd graph, no triangular solves):
-             Q_0 = Kinv, Q_r = B_r B_r^T with B_r = Kinv L_r, beta = Kinv q_mu       (Kinv = Kuu^-1)
-             KL  = 1/2 [q_mu^T Kp^-1 q_mu - MR - sum log diag(L_r)^2 + sum <L_r, Kp^-1 L_r> + R log|Kp|]
+    def m_only(self, kl_weight=1.0, hyp=None, static=None):
+        """Chain rule through the minibatch-independent operands, in the order of the forward (conditionals.py:29-58):
+             Lm = chol(Kuu), Li = Lm^-1, a = Li k;  C_r = Li L_r (L_r when whitened), S_r = C_r C_r^T, alpha = Li q_mu (q_mu)
+           mean_r = alpha_r^T a,  var_r = knn - |a|^2 + a^T S_r a.
+        Inputs (dcgp_layer_backward): dS_r = sum_t s_r a a^T, dalpha = sum_t a g_mean^T, and the direct paths gZ, gscal, gw.
+          H  = sum_t da_t a_t^T = alpha dalpha^T + sum_r 2 (S_r - I) dS_r                    (d/dLi through a = Li k is H Lm^T)
+          W  = H + sum_r 2 dS_r S_r + dalpha alpha^T    (non-whitened: C_r and alpha move with Li as well),  d/dLi = W Lm^T
+          dLm = tril(-Li^T W),  dKuu = 1/2 Li^T (P + P^T) Li  with P = Phi(Lm^T dLm)          (Cholesky backward; Phi: tril, diag/2)
+          d/dL_r = tril(Li^T 2 dS_r C_r)  (tril(2 dS_r C_r) whitened),  d/dq_mu = Li^T dalpha  (dalpha whitened)
+        Returns d ELBO / d{Z, variance, lengthscale, q_mu, q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that
+        summing over ranks counts the KL once.  `hyp` (optional): device tensor [variance, lengthscale] to use instead of the
+        host floats -- keeps the whole chain free of host values so that it can be captured in a CUDA graph (TrainStep).
         `static` = the result of m_only_static() for the same parameters (computed here when absent)."""
         layer = self.layer
         M, R, Mp = self.M, self.R, self.Mp
+        white = layer.white
         st = static if static is not None else self.m_only_static(kl_weight, hyp)
         bt = self.BATCHED_DTYPE
-        gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
-        gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
-        Kinv = st["Kinv"]
-        Ub = self._bmm((gQ[1:] + gQ[1:].transpose(1, 2)).to(bt), st["Bb"])   # d/dB_r
-        gLq = self._left(st["Kinvb"], Ub).to(torch.float64) + st["gLq_kl"]   # d/dL_r (through B_r) + KL
-        GK = gQ[0] + self._bsum(Ub, st["Lqb"]).to(torch.float64) + gbeta @ st["q_mu"].T   # d/dKinv
-        g_qmu = Kinv @ gbeta + st["g_qmu_kl"]
-        GU = -(Kinv @ GK @ Kinv)                                         # d/dKuu
+        gS = self.gQB[Mp:(R + 1) * Mp].reshape(R, Mp, Mp)[:, :M, :M]
+        galpha = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T              # [M, R]
+        gSb = gS.to(bt)
+        Tm = self._bmm(st["Sb"], gSb)                                       # S_r dS_r
+        Tsum = Tm.sum(0).to(torch.float64)
+        alpha, Li, LiT, Lm = st["alpha"], st["Li"], st["LiT"], st["Lm"]
+        H = alpha @ galpha.T + 2.0 * (Tsum - gS.sum(0))
+        GC = 2.0 * self._bmm(gSb, st["Cb"])                                 # d/dC_r
+        if white:
+            W = H
+            gLq = GC.to(torch.float64) + st["gLq_kl"]
+            g_qmu = galpha + st["g_qmu_kl"]
+        else:
+            W = H + 2.0 * Tsum.T + galpha @ alpha.T
+            gLq = self._left(st["LiTb"], GC).to(torch.float64) + st["gLq_kl"]
+            g_qmu = LiT @ galpha + st["g_qmu_kl"]
+        P = torch.tril(Lm.T @ torch.tril(-(LiT @ W)))
+        P = P - 0.5 * torch.diag_embed(torch.diagonal(P))
+        GU = 0.5 * (LiT @ (P + P.T) @ Li)                                   # d/dKuu
         if st["GU_kl"] is not None:
             GU = GU + st["GU_kl"]
         gvar, gls, gZ = self._rbf_chain(GU, st["Kn"], st["D"], st["Z"], st["var"], st["ls"])
         out = {"Z": gZ + self.gZ, "variance": gvar + st["gvar_p"] + self.gscal[0],
                "lengthscale": gls + st["gls_p"] + self.gscal[1], "q_mu": g_qmu, "q_sqrt": torch.tril(gLq)}
-        if layer._kind == _lib.LAYER_SVGP_CONV:
-            out["patch_weights"] = self.gw.clone()
-        return out
-
-    def _m_only_autograd(self, kl_weight=1.0):
-        """Whitened case (non-default, arguments.py:33): torch.autograd over the same float64 algebra."""
-        layer = self.layer
-        dev = layer.device
-        M, R, Mp = self.M, self.R, self.Mp
-        gQ = self.gQB[:(R + 1) * Mp].reshape(R + 1, Mp, Mp)[:, :M, :M]
-        gbeta = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T            # [M, R]
-        with torch.enable_grad():
-            Z = layer.feature.Z.detach().to(torch.float64).clone().requires_grad_(True)
-            var = torch.tensor(float(layer._base_kernel.variance), dtype=torch.float64, device=dev, requires_grad=True)
-            ls = torch.tensor(float(layer._base_kernel.lengthscales), dtype=torch.float64, device=dev, requires_grad=True)
-            q_mu = layer.q_mu.detach().clone().requires_grad_(True)
-            q_sqrt = layer.q_sqrt.detach().clone().requires_grad_(True)
-            eye = torch.eye(M, dtype=torch.float64, device=dev)
-            Kuu = _rbf(Z, var, ls) + JITTER * eye
-            Lq = torch.tril(q_sqrt)
-            logdet_q = torch.log(torch.diagonal(Lq, dim1=1, dim2=2) ** 2).sum()
-            Lm = torch.linalg.cholesky(Kuu)
-            Linv = torch.linalg.solve_triangular(Lm, eye, upper=False)
-            Kinv = Linv.T @ Linv
-            B = Linv.T @ Lq
-            beta = Linv.T @ q_mu
-            kl = 0.5 * ((q_mu ** 2).sum() - M * R - logdet_q + (Lq ** 2).sum())
-            obj = (gQ[0] * Kinv).sum() + (gQ[1:] * (B @ B.transpose(1, 2))).sum() + (gbeta * beta).sum() - kl_weight * kl
-            gZ, gvar, gls, gq_mu, gq_sqrt = torch.autograd.grad(obj, [Z, var, ls, q_mu, q_sqrt])
-        out = {"Z": gZ + self.gZ, "variance": gvar + self.gscal[0], "lengthscale": gls + self.gscal[1], "q_mu": gq_mu,
-               "q_sqrt": torch.tril(gq_sqrt)}
         if layer._kind == _lib.LAYER_SVGP_CONV:
             out["patch_weights"] = self.gw.clone()
         return out
@@ -551,7 +524,7 @@ class TrainStep(object):
         """Run fn() on the current stream: eagerly for the first GRAPH_AFTER calls, then captured once and replayed as a
         single CUDA-graph launch (fixed shapes and pointers, no host values inside)."""
         layer = self.model.layers[i]
-        if not self.use_graphs or layer.white:
+        if not self.use_graphs:
             return fn()
         g = self._graphs[key].get(i)
         if g is not None:
@@ -568,8 +541,6 @@ class TrainStep(object):
     def _m_only_static(self, i, wsize):
         """Parameter-only part of layer i's chain rule (LayerBackward.m_only_static) on the current stream."""
         eg, opt = self.eg, self.opt
-        if self.model.layers[i].white:
-            return
 
         def run():
             hyp = torch.nn.functional.softplus(opt.hyp_slice(i)) + 1e-6       # == the values the host holds

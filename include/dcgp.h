@@ -126,9 +126,14 @@ size_t dcgp_prepare_workspace_bytes(const dcgp_layer_desc* d);
 /* Byte offsets, inside the workspace of the last dcgp_layer_prepare (algo = DCGP_ALGO_TC), of float64 results the host-side
  * chain rule re-uses: Kuu^-1 [M,M] (ld M), Lm^-1 and the prior's Lp^-1 (lower triangular, ld = *ld_inv >= M). */
 int dcgp_prepare_workspace_layout(const dcgp_layer_desc* d, size_t* off_kinv, size_t* off_linv, size_t* off_lpinv, int* ld_inv);
-/* Offset (bytes) inside the `prep` buffer of B_r = G L_r as float32 [R, ld_b, ld_b] (tensor-core path, non-whitened:
- * G = Kuu^-1), left there by dcgp_layer_prepare for the host-side M-only chain rule. */
+/* Offset (bytes) inside the `prep` buffer of C_r = Lm^-1 L_r (L_r when whitened) as float32 [R, ld_b, ld_b] (tensor-core path),
+ * left there by dcgp_layer_prepare for the host-side M-only chain rule. */
 int dcgp_prepare_layout(const dcgp_layer_desc* d, size_t* off_b32, int* ld_b);
+/* The same plus S_r = C_r C_r^T (float32 [R, ld, ld]); and the workspace layout plus the Cholesky factor Lm (lower triangle of
+ * the [M, M] block at *off_lm, leading dimension M; the strict upper triangle is scratch). */
+int dcgp_prepare_layout2(const dcgp_layer_desc* d, size_t* off_c32, size_t* off_s32, int* ld);
+int dcgp_prepare_workspace_layout2(const dcgp_layer_desc* d, size_t* off_kinv, size_t* off_linv, size_t* off_lpinv, size_t* off_lm,
+                                   int* ld_inv);
 int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
                        const double* q_sqrt, int algo, void* prep, double* kl, void* ws, size_t ws_bytes,
                        int* info, void* stream);
@@ -159,8 +164,9 @@ int dcgp_layer_apply(const dcgp_layer_desc* d, const void* prep, const double* p
  *                    (the forward leaves the kernel-matrix planes in apply_ws).
  *   g_mean, g_var  : [n_rows*n_rep, D] float32 gradients w.r.t. the layer's mean / var outputs.
  *   gX   [n_rows, H*W*C] float32, or NULL when the input needs no gradient (first layer)
- *   gQB  [(R+1)*Mp + 64, Mp] float64, Mp = M rounded up to 64: rows blk*Mp + i hold dQ_blk[i, :] where
- *        acc_blk(t) = k_t^T Q_blk k_t (Q_0 = Kuu^-1, Q_r = G L_r L_r^T G^T), rows (R+1)*Mp + r hold dbeta[:, r]
+ *   gQB  [(R+1)*Mp + 64, Mp] float64, Mp = M rounded up to 64: rows r*Mp + i (r = 1..R) hold dS_r[i, :] = sum_t s_r(t) a_t a_t^T
+ *        (a_t = Lm^-1 k_t; var_r = knn - |a|^2 + a^T S_r a, S_r = C_r C_r^T), block 0 holds -sum_r dS_r; rows (R+1)*Mp + r
+ *        hold dalpha[:, r] = sum_t g_mean_r(t) a_t   (mean_r = alpha_r^T a)
  *   gZ   [M, L] float64: direct path through Kuf;   gscal[4]: {d/dvariance, d/dlengthscale, -, -} direct paths
  *   gw   [P] float64 (SVGP_CONV only).  The M-only chain rule (Q, beta, KL -> Z, hyper-parameters, q_mu, q_sqrt) is
  *        small dense float64 algebra done by the host (deepcgp_b200/grad.py). */

@@ -84,7 +84,7 @@ def test_bench_model_forward_elbo_gradients_vs_oracle(cfg_name, N, S):
         assert any(frag in n for n in names), (frag, sorted(n for n in names if "dcgp" in n)[:40])
 
 
-@pytest.mark.parametrize("prods", [(3, 3, 3), (1, 1, 1), (2, 2, 2)])
+@pytest.mark.parametrize("prods", [(3, 3, 3), (1, 3, 3), (3, 1, 3), (3, 3, 1), (2, 3, 3), (3, 2, 3), (3, 3, 2), (1, 1, 1)])
 def test_split_product_settings_meet_the_gates(prods):
     """dcgp_set_products: every setting the library offers must meet the forward gate (1e-4) and the gradient gate on the
     benchmark model (cfg3 shapes); the default is whatever passes with margin (precision)."""
