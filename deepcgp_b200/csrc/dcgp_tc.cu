@@ -160,7 +160,7 @@ struct TcParams {
   int n_items;
   int nkb;        // K-dimension blocks of 64
   int nprod;      // split products per k-step: 3 = Al*Bh + Ah*Bl + Ah*Bh (22-bit operands), 2 = Al*Bh + Ah*Bh (A 22 bits, B 11),
-                  // 1 = Ah*Bh (11-bit operands); the planes that are not multiplied are not loaded either
+                  // 4 = Ah*Bl + Ah*Bh (A 11 bits, B 22), 1 = Ah*Bh (11-bit operands); planes that are not multiplied are not loaded
   int bf16;       // MODE_GEMM: operand planes are bf16 (hi + lo) instead of fp16
   // ---- MODE_COND
   int T;          // valid patch-columns
@@ -262,8 +262,8 @@ constexpr int kMaxStages = 8;
 template <int BN>
 __device__ __forceinline__ void ring_geom(int nprod, int& a_planes, int& b_planes, int& stage_bytes, int& n_stages) {
   using Cfg = CondCfg<BN>;
-  a_planes = nprod >= 2 ? 2 : 1;
-  b_planes = nprod >= 3 ? 2 : 1;
+  a_planes = (nprod == 2 || nprod == 3) ? 2 : 1;
+  b_planes = nprod >= 3 ? 2 : 1;                 // nprod = 4: A hi only, B hi + lo (Ah*Bl + Ah*Bh)
   stage_bytes = a_planes * Cfg::kStageA + b_planes * Cfg::kStageB;
   n_stages = min(kMaxStages, (Cfg::kStages * Cfg::kStageBytes) / stage_bytes);
 }
@@ -309,7 +309,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         const bool desc = tile_descending<MODE, BN>(p, item);
         // MODE_COND mean rows (alpha^T a): always the full 22-bit product.  With fewer than four plane slots per stage the
         // k-range is walked three times with single planes in the hi slots: (A_lo, B_hi), (A_hi, B_lo), (A_hi, B_hi).
-        const bool mean3 = mean_item<MODE, BN>(p, item) && p.nprod < 3;
+        const bool mean3 = mean_item<MODE, BN>(p, item) && p.nprod != 3;
         for (int jt = 0; jt < njt; ++jt) {
           int arow, brow, kb0, kb1;
           tile_rows<MODE, BN>(p, item, jt, arow, brow);
@@ -355,7 +355,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int njt = tiles_in_item<MODE, BN>(p, item);
         const bool desc = tile_descending<MODE, BN>(p, item);
-        const bool mean3 = mean_item<MODE, BN>(p, item) && p.nprod < 3;
+        const bool mean3 = mean_item<MODE, BN>(p, item) && p.nprod != 3;
         const bool two_a = !mean3 && a_planes == 2, two_b = !mean3 && b_planes == 2;
         for (int jt = 0; jt < njt; ++jt, ++tile) {
           const uint32_t buf = tile & 1, use = tile >> 1;
@@ -620,7 +620,7 @@ static TcProducts g_prod = {0, 0, 0};
 static int env_prod(const char* name, int dflt) {
   const char* e = getenv(name);
   const int v = e ? atoi(e) : dflt;
-  return (v >= 1 && v <= 3) ? v : dflt;
+  return (v >= 1 && v <= 4) ? v : dflt;
 }
 const TcProducts& tc_products() {
   if (!g_prod.cond) {
@@ -632,9 +632,9 @@ const TcProducts& tc_products() {
 }
 void tc_set_products(int cond, int dk, int dq) {
   tc_products();
-  if (cond >= 1 && cond <= 3) g_prod.cond = cond;
-  if (dk >= 1 && dk <= 3) g_prod.dk = dk;
-  if (dq >= 1 && dq <= 3) g_prod.dq = dq;
+  if (cond >= 1 && cond <= 4) g_prod.cond = cond;
+  if (dk >= 1 && dk <= 4) g_prod.dk = dk;
+  if (dq >= 1 && dq <= 4) g_prod.dq = dq;
 }
 
 static int num_sms() {
@@ -656,7 +656,7 @@ template <int MODE, int BN>
 static int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUtensorMap& tmBh, const CUtensorMap& tmBl,
                      const CUtensorMap& tmB64h, const CUtensorMap& tmB64l, const TcParams& p, cudaStream_t st) {
   using Cfg = CondCfg<BN>;
-  if (p.nprod < 1 || p.nprod > 3) { set_error("tc_kernel: nprod must be 1, 2 or 3"); return DCGP_ERR_ARG; }
+  if (p.nprod < 1 || p.nprod > 4) { set_error("tc_kernel: nprod must be 1 .. 4"); return DCGP_ERR_ARG; }
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(tc_kernel<MODE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -737,11 +737,12 @@ static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, i
   if ((rc = check_launch("set_scale"))) return rc;
   ScopedTimer timer(0, st);
   const int nprod2 = tc_products().cond;
+  const int nmul2 = nprod2 == 4 ? 2 : nprod2;
   {   // executed tensor flops of the two launches: 64-column granularity on the triangular operands
     const int nb = Mp / kBK;                                   // 64-blocks per side
     const double tri_blocks = 0.5 * nb * (nb + 1);             // (k-block, 64-column block) pairs that are not structurally zero
     const double per_blk = 2.0 * (double)w.Tpad * kBK * kBK;   // one 64 x 64 block pair over all patch columns
-    timer.flops(3 * per_blk * tri_blocks + nprod2 * per_blk * tri_blocks * R + 3 * 2.0 * (double)w.Tpad * BN * Mp);
+    timer.flops(3 * per_blk * tri_blocks + nmul2 * per_blk * tri_blocks * R + 3 * 2.0 * (double)w.Tpad * BN * Mp);
   }
   TcParams p;
   memset(&p, 0, sizeof(p));

@@ -71,11 +71,12 @@ double dcgp_kernel_ms(int which);
  * launcher: the "executed" figure next to the algorithmic one in bench.py's roofline. */
 double dcgp_kernel_tensor_flops(int which);
 /* Precision of the three big T-sized GEMM families on the tensor-core path.  Every operand is held as two fp16 planes
- * x = hi + lo (22 bits); a GEMM issues 3 products per k-step (Al*Bh + Ah*Bl + Ah*Bh: fp32-class), 2 (Al*Bh + Ah*Bh) or 1
- * (Ah*Bh: fp16 operands, fp32 accumulation).  cond = second stage of the forward conditional (G_r = C_r^T a, which only feeds
- * a sum of squares; the first stage a = Lm^-1 k, where cancellation happens, always uses 3), dk / dq = the two large
- * backward GEMMs (conditionals.py:31-65 differentiated).  0 leaves a value unchanged.  Defaults: env DCGP_PROD_COND /
- * DCGP_PROD_DK / DCGP_PROD_DQ, else the library's built-in choice (dcgp_get_products reports the values in force). */
+ * x = hi + lo (22 bits); a GEMM issues per k-step: 3 = Al*Bh + Ah*Bl + Ah*Bh (fp32-class), 2 = Al*Bh + Ah*Bh (B rounded to
+ * fp16), 4 = Ah*Bl + Ah*Bh (A rounded to fp16), 1 = Ah*Bh (fp16 operands); fp32 accumulation throughout.  cond = second stage of
+ * the forward conditional (G_r = C_r^T a, A = a; the first stage a = Lm^-1 k, where cancellation happens, always uses 3),
+ * dk = da = sum_r s_r a SP_r (A = a), dq = dS_r = a^T diag(s_r) a -- the large GEMMs of conditionals.py:31-65 and of its
+ * derivative.  0 leaves a value unchanged.  Defaults: env DCGP_PROD_COND / DCGP_PROD_DK / DCGP_PROD_DQ, else the library's
+ * built-in choice (3, 4, 3); dcgp_get_products reports the values in force. */
 void dcgp_set_products(int cond, int dk, int dq);
 void dcgp_get_products(int* cond_host, int* dk_host, int* dq_host);
 

@@ -144,7 +144,7 @@ def test_layer_backward_pieces_vs_float64_autograd(cfg_name, li, N):
     errs, _, _, _, _, _ = _run_layer(li, N, cfg_name=cfg_name)
     print("\n%s layer %d pieces, normwise: %s" % (cfg_name, li, {k: "%.1e" % v for k, v in errs.items()}))
     for k, e in errs.items():
-        assert e <= 1e-4, (k, e)
+        assert e <= (1e-4 if cfg_name == "cfg3" else 3e-4), (k, e)
 
 
 @pytest.mark.parametrize("cfg_name,li,N,white", [("cfg3", 1, 6, False), ("cfg3", 2, 6, False), ("cfg3", 1, 4, True), ("cfg4", 1, 4, False)])

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -rP > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
 tail -5 gpurun_out/${tag}_pytest.log
-for pr in 133 313 331; do
+for pr in 333 311 113 111; do
   c=${pr:0:1}; k=${pr:1:1}; q=${pr:2:1}
   DCGP_PROD_COND=$c DCGP_PROD_DK=$k DCGP_PROD_DQ=$q timeout 600 python bench.py --steps 10 --warmup 3 --no-extras \
       > gpurun_out/${tag}_bench_${pr}.json 2> gpurun_out/${tag}_bench_${pr}.err
