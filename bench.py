@@ -591,28 +591,33 @@ def kernel_roofline(model, cfg, B, S, device, flush):
     kuf_bytes = 4.0 * T * M + 4.0 * n_rows * X.shape[1]      # K planes written (hi+lo fp16) + images read
     src = "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590"
 
-    def prof(key):
-        e = ncu.get(key, {})
-        return {"traffic": e.get("dram_bytes"), "tensor_pipe_active_pct_ncu": e.get("tensor_pipe_active_pct"),
+    def prof(key, also=None):
+        """DRAM bytes (summed over the launches a timed entry spans) and tensor-pipe activity of the dominant launch."""
+        e, e2 = ncu.get(key, {}), ncu.get(also, {}) if also else {}
+        traffic = e.get("dram_bytes")
+        if traffic is not None and e2.get("dram_bytes") is not None:
+            traffic += e2["dram_bytes"]
+        return {"traffic": traffic, "tensor_pipe_active_pct_ncu": e.get("tensor_pipe_active_pct"),
                 "ncu_source": ncu.get("source")}
 
-    def tensor_entry(name, key, t_ms, alg_flops, exe_flops):
+    def tensor_entry(name, key, t_ms, alg_flops, exe_flops, also=None):
         e = {"kernel": name, "bound": "tensor", "ms": t_ms, "achieved": alg_flops / (t_ms * 1e-3) / 1e12, "peak": peak,
              "unit": "TFLOP/s", "frac": alg_flops / (t_ms * 1e-3) / 1e12 / peak, "algorithmic_gflop": alg_flops / 1e9,
              "executed_tensor_gflop": exe_flops / 1e9, "executed_frac": exe_flops / (t_ms * 1e-3) / 1e12 / peak}
-        e.update(prof(key))
+        e.update(prof(key, also))
         return e
 
     # backward GEMMs: algorithmic = the Q-form contraction 2*T*R*M^2 (dQ: its symmetric half)
-    dk = tensor_entry("dk_gemm_kernel<256,true> (dK GEMM + fused dd epilogue, conv layer 2 backward)", "dk_gemm", ms_dk,
-                      2.0 * T * R * M * M, exe[2])
-    dq = tensor_entry("xf_gemm_kernel<256> (dQ GEMM, conv layer 2 backward)", "dq_gemm", ms_dq, 1.0 * T * R * M * M, exe[3])
+    # (dK: da = sum_r s_r a SP_r, then dK = da Lm^-1 with the fused dd epilogue -- two launches timed together)
+    dk = tensor_entry("dk_gemm_kernel<256,EPI_PLANES> + dk_gemm_kernel<256,EPI_DD> (da GEMM, then dK = da Lm^-1 + fused dd epilogue; "
+                      "conv layer 2 backward)", "dk_gemm", ms_dk, 2.0 * T * R * M * M + 1.0 * T * M * M, exe[2], also="dk_gemm_stage2")
+    dq = tensor_entry("xf_gemm_kernel<256> (dS_r = a^T diag(s_r) a, conv layer 2 backward)", "dq_gemm", ms_dq, 1.0 * T * R * M * M, exe[3])
     out = {"bound": "tensor", "kernel": "tc_kernel<MODE_A,256> + tc_kernel<MODE_COND,256> (chained conditional GEMM, conv layer 2 forward)",
            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "ms": ms, "algorithmic_gflop": alg / 1e9,
            "executed_tensor_gflop": exe[0] / 1e9, "executed_tflops": exe[0] / (ms * 1e-3) / 1e12,
            "executed_frac": exe[0] / (ms * 1e-3) / 1e12 / peak, "peak_source": src,
            "input": "samples of conv layer 1 (the layer's actual input in the benchmark state)"}
-    out.update(prof("cond_gemm"))
+    out.update(prof("cond_gemm", "cond_gemm_stage1"))
     kuf = {"kernel": "kuf_tc_kernel<256> (conv layer 2)", "bound": "hbm", "ms": ms_kuf,
            "achieved": kuf_bytes / (ms_kuf * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
            "frac": kuf_bytes / (ms_kuf * 1e-3) / 1e9 / hbm, "algorithmic_bytes": kuf_bytes,

@@ -17,9 +17,9 @@ def default_algo():
 from .views import FullView, View  # noqa: E402,F401
 from .kernels import RBF, ConvKernel, AdditivePatchKernel, PatchInducingFeatures, Kuu, Kuf  # noqa: E402,F401
 from .conditionals import conditional  # noqa: E402,F401
-from .layers import ConvLayer, Layer, MultiOutputConvKernel, SVGP_Layer, Zero  # noqa: E402,F401
+from .layers import Conv2dMean, ConvLayer, Layer, MultiOutputConvKernel, SVGP_Layer, Zero  # noqa: E402,F401
 from .likelihoods import BroadcastingLikelihood, MultiClass  # noqa: E402,F401
 from .dgp import DGP_Base  # noqa: E402,F401
-from .grad import Adam, ElboGradient, TrainStep  # noqa: E402,F401
+from .grad import Adam, ElboGradient, NatGrad, TrainStep  # noqa: E402,F401
 from .models import ModelBuilder, save_model_parameters  # noqa: E402,F401
 from .experiment import Experiment, accuracy, exponential_decay, train_steps  # noqa: E402,F401

@@ -38,6 +38,7 @@ SIGNATURES = {
     "dcgp_version": (_i, []),
     "dcgp_launch_count": (C.c_longlong, []),
     "dcgp_set_kernel_timing": (None, [_i]),
+    "dcgp_set_reserved_sms": (None, [_i]),
     "dcgp_kernel_ms": (C.c_double, [_i]),
     "dcgp_kernel_tensor_flops": (C.c_double, [_i]),
     "dcgp_set_products": (None, [_i, _i, _i]),

@@ -222,6 +222,7 @@ const char* dcgp_last_error(void) { return dcgp::last_error(); }
 int dcgp_version(void) { return 100; }
 long long dcgp_launch_count(void) { return dcgp::launch_count(); }
 void dcgp_set_kernel_timing(int on) { dcgp::tc_set_timing(on); }
+void dcgp_set_reserved_sms(int n) { dcgp::tc_set_reserved_sms(n); }
 double dcgp_kernel_ms(int which) { return dcgp::tc_kernel_ms(which); }
 double dcgp_kernel_tensor_flops(int which) { return dcgp::tc_kernel_flops(which); }
 void dcgp_set_products(int cond, int dk, int dq) { dcgp::tc_set_products(cond, dk, dq); }

@@ -648,6 +648,14 @@ static int num_sms() {
   return n;
 }
 
+// SMs the persistent tensor kernels leave free (grid = SMs - reserve).  A host that runs latency-critical small kernels on
+// another stream underneath a long persistent GEMM (grad.TrainStep: a layer's chain rule + optimiser update + next-step
+// prepare under the parameter-only GEMMs of the layers above) sets it around those launches: CTAs of a persistent kernel
+// never yield, so without free SMs the other stream only advances in the gaps between kernels.
+static int g_reserve_sms = 0;
+void tc_set_reserved_sms(int n) { g_reserve_sms = n < 0 ? 0 : n; }
+static int grid_sms() { const int n = num_sms() - g_reserve_sms; return n < 1 ? 1 : n; }
+
 constexpr int kWPadRows = 256;   // zero rows after the mean block so a BN-row box never leaves the tensor
 
 static size_t w_rows(int Mp, int R) { return (size_t)(R + 1) * Mp + kWPadRows; }
@@ -663,7 +671,7 @@ static int launch_tc(const CUtensorMap& tmAh, const CUtensorMap& tmAl, const CUt
     if (e != cudaSuccess) { set_error("tc_kernel smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
     attr = true;
   }
-  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  const int grid = p.n_items < grid_sms() ? p.n_items : grid_sms();
   if (grid <= 0) return DCGP_OK;
   tc_kernel<MODE, BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmAh, tmAl, tmBh, tmBl, tmB64h, tmB64l, p);
   return check_launch("tc_kernel");

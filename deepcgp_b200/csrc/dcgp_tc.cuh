@@ -90,6 +90,7 @@ int tc_layer_apply(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, 
                    float* Kt32, const double* patch_weights, const float* X, int n_rows, float* Kzx, float* acc,
                    float* mean_t, cudaStream_t st);
 
+void tc_set_reserved_sms(int n);
 void tc_set_timing(int on);
 double tc_kernel_ms(int which);   // 0 = conditional GEMM, 1 = Kuf, 2 = dK (+dd) GEMM, 3 = dQ GEMM (last launch of each)
 double tc_kernel_flops(int which);   // executed tensor-pipe flops of that launch (counted by the launcher)

@@ -1,13 +1,17 @@
 """Training driver -- host-side mirror of conv_gp/experiment.py:13-136 for the default optimiser (`--optimizer Adam`):
 learning-rate schedule (:71-73), the optimisation loop of `test_every` iterations (:38-44), the accuracy logger
-(conv_gp/utils/log.py:50-68) and the parameter dump (:56-64).  SURVEY.md 8 rows f2/f4; NatGrad (:91-99) is not built.
+(conv_gp/utils/log.py:50-68) and the parameter dump (:56-64); `--optimizer SGD` (:101-104) and the NatGrad + Adam hybrid
+(:88-99) with its gamma schedule (:74-81) and Cholesky-failure back-off (:38-49).  SURVEY.md 8 rows f2/f4.
 """
 import math
 import os
 
 import numpy as np
 
-from .grad import TrainStep
+import torch
+
+from . import _lib
+from .grad import Adam, ElboGradient, NatGrad, TrainStep
 from .models import ModelBuilder, save_model_parameters
 
 
@@ -47,8 +51,9 @@ class Experiment(object):
     lr_decay_steps, test_every, batch_size, M, ...)."""
 
     def __init__(self, flags, X_train, Y_train, X_test=None, Y_test=None, device="cuda", seed=0):
-        if getattr(flags, "optimizer", "Adam") != "Adam":
-            raise NotImplementedError("only --optimizer Adam (the default, arguments.py:25) is built")
+        self.optimizer = getattr(flags, "optimizer", "Adam")
+        if self.optimizer not in ("Adam", "NatGrad", "SGD"):
+            raise ValueError("Not a supported optimizer. Try Adam or NatGrad.")          # experiment.py:110-111
         self.flags = flags
         self.X_train, self.Y_train = np.asarray(X_train), np.asarray(Y_train)
         self.X_test, self.Y_test = X_test, Y_test
@@ -56,7 +61,16 @@ class Experiment(object):
         builder = ModelBuilder(flags, self.X_train, self.Y_train, model_path=path, device=device, seed=seed)
         self.model = builder.build()                                          # _setup_model
         self.global_step = int(builder.global_step or 0)
-        self.step = TrainStep(self.model, lr=flags.lr)                        # _setup_optimizer (Adam)
+        self.steps_back = 0                                                   # experiment.py:79 (gamma back-off counter)
+        if self.optimizer == "Adam":                                          # _setup_optimizer
+            self.step = TrainStep(self.model, lr=flags.lr)
+        else:
+            # NatGrad: the variational parameters belong to the natural-gradient action and are frozen for Adam (:88-99)
+            self.eg = ElboGradient(self.model)
+            self.opt = Adam(self.model, lr=flags.lr, frozen=("q_mu", "q_sqrt") if self.optimizer == "NatGrad" else (),
+                            sgd=self.optimizer == "SGD")
+            self.opt.bind()
+            self.natgrad = NatGrad(self.model) if self.optimizer == "NatGrad" else None
         self.entries = []
 
     def _model_path(self, model_name=None):
@@ -65,14 +79,61 @@ class Experiment(object):
     def learning_rate(self):
         return exponential_decay(self.flags.lr, self.global_step, self.flags.lr_decay_steps)
 
-    def _optimize(self):
-        """Loop(self.loop, stop=test_every)(): `test_every` Adam iterations on successive minibatches."""
-        for _ in range(self.flags.test_every):
-            self.step.opt.lr = self.learning_rate()
-            X, Y = self.model._next_batch()
-            self.last_elbo = self.step(np.asarray(X).reshape(len(X), -1).astype(np.float32), Y)
+    def gamma(self):
+        """experiment.py:74-81: min((global_step / 100 * 1e-3 + flags.gamma) * 0.2 ** steps_back, 1)."""
+        t = self.global_step / 100.0
+        return min((t * 1e-3 + getattr(self.flags, "gamma", 1e-3)) * 0.2 ** self.steps_back, 1.0)
+
+    def _batch(self):
+        X, Y = self.model._next_batch()
+        return np.asarray(X).reshape(len(X), -1).astype(np.float32), Y
+
+    def _checked_gradient(self):
+        """One ELBO + gradient evaluation; a failed Cholesky of Kuu or a non-finite ELBO is the reference's
+        tf.errors.InvalidArgumentError at session.run."""
+        X, Y = self._batch()
+        elbo, grads = self.eg(X, Y)
+        for layer in self.model.layers:
+            _lib.raise_if_not_pd(layer._info)
+        if not bool(torch.isfinite(elbo)):
+            raise _lib.NotPositiveDefiniteError("non-finite ELBO")
+        return elbo, grads
+
+    def _iterations(self, numiter):
+        """Loop(self.loop, stop=numiter)(): the loop's actions run one after the other, each on its own minibatch."""
+        if self.optimizer == "Adam":
+            for _ in range(numiter):
+                self.step.opt.lr = self.learning_rate()
+                X, Y = self._batch()
+                self.last_elbo = self.step(X, Y)
+                self.global_step += 1
+            self.step.finish()
+            for layer in self.model.layers:          # never write a checkpoint from a step that went wrong
+                _lib.raise_if_not_pd(layer._info)
+            if not bool(torch.isfinite(self.last_elbo)):
+                raise FloatingPointError("non-finite ELBO at global step %d" % self.global_step)
+            return
+        for _ in range(numiter):
+            if self.natgrad is not None:
+                _, grads = self._checked_gradient()
+                self.natgrad.step(grads, self.gamma())
+            self.opt.lr = self.learning_rate()
+            self.last_elbo, grads = self._checked_gradient()
+            self.opt.step(grads)
             self.global_step += 1
-        self.step.finish()
+
+    def _optimize(self, retry=0, error=None):
+        """experiment.py:38-49: `test_every` iterations; with NatGrad a failed Cholesky shrinks gamma by 0.2 and the loop is
+        started again, at most five times."""
+        if retry > 5:
+            raise error
+        try:
+            self._iterations(self.flags.test_every)
+        except _lib.NotPositiveDefiniteError as exception:
+            if self.optimizer != "NatGrad":
+                raise
+            self.steps_back += 1                                              # step_back_gamma
+            self._optimize(retry=retry + 1, error=exception)
 
     def train_step(self):
         """experiment.py:28-31"""

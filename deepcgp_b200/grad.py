@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .dist import allreduce_sum_, shard_range, world
 from .kernels import JITTER
-from .layers import ConvLayer
+from .layers import Conv2dMean, ConvLayer
 
 
 def _rbf(Z, variance, lengthscale):
@@ -65,6 +65,10 @@ class LayerBackward(object):
         w = layer._patch_weights()
         self._keep = (X, g_mean, g_var, w, gX, ws, aws, d, n_rows, n_rep)
         self._call(phases)
+        mf = getattr(layer, "mean_function", None)
+        if gX is not None and isinstance(mf, Conv2dMean):      # the fixed mean function passes g_mean straight to its taps
+            v = layer._view
+            gX += mf.backward(g_mean, int(v.input_size[0]), int(v.input_size[1]))
         return gX
 
     def t_sized_rest(self):
@@ -341,8 +345,12 @@ class Adam(object):
 
     NAMES = ("Z", "variance", "lengthscale", "q_mu", "q_sqrt", "patch_weights")
 
-    def __init__(self, model, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+    def __init__(self, model, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8, frozen=(), sgd=False):
+        """frozen: parameter names excluded from the update (`param.set_trainable(False)`, experiment.py:91-94: the
+        variational parameters when the natural-gradient optimiser owns them).  sgd: plain gradient ascent with step lr
+        (gpflow.train.GradientDescentOptimizer, experiment.py:101-104) instead of the Adam rule."""
         self.model, self.lr, self.b1, self.b2, self.eps = model, lr, beta1, beta2, eps
+        self.frozen, self.sgd = tuple(frozen), bool(sgd)
         self.step_no = 0
         dev = model.device
         self.slots = []
@@ -419,6 +427,9 @@ class Adam(object):
                 continue
             g = grads[li][name]
             dst = self._view(self.grad, slot)
+            if name in self.frozen:
+                dst.zero_()
+                continue
             if name in ("variance", "lengthscale"):
                 u = self._view(self.flat, slot)
                 dst.copy_((g * torch.sigmoid(u)).reshape(1))          # d softplus(u) / du
@@ -488,9 +499,65 @@ class Adam(object):
         self._store_grads(grads)
         self._allreduce_slice(0, self.n)                                # the single exchange of the image-sharded step
         self.step_no += 1
-        _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v), self.n,
-                                      self.lr, self.b1, self.b2, self.eps, self.step_no, 1, _lib.stream()))
+        if self.sgd:
+            self.flat.add_(self.grad, alpha=self.lr)                    # ascent on the ELBO
+        else:
+            _lib.check(_lib.lib.dcgp_adam(_lib.ptr(self.flat), _lib.ptr(self.grad), _lib.ptr(self.m), _lib.ptr(self.v), self.n,
+                                          self.lr, self.b1, self.b2, self.eps, self.step_no, 1, _lib.stream()))
         self._push()
+
+
+class NatGrad(object):
+    """gpflow.train.NatGradOptimizer(gamma) on every layer's (q_mu, q_sqrt) (experiment.py:88-99), default xi = natural
+    parameters: with L = -ELBO, theta = (S^-1 mu, -1/2 S^-1), eta = (mu, S + mu mu^T),
+        theta <- theta - gamma dL/deta,      dL/deta_2 = dL/dS =: G,   dL/deta_1 = dL/dmu - 2 G mu,
+    where dL/dS follows from dL/dq_sqrt by the Cholesky backward rule (S = L L^T).  The step leaves q(u) Gaussian only while
+    -2 theta_2 stays positive definite; otherwise the Cholesky of the new covariance fails -- the reference's
+    tf.errors.InvalidArgumentError (experiment.py:45-49) -- and NotPositiveDefiniteError is raised with the parameters
+    untouched, for the caller's gamma back-off.  M-only float64 algebra (R x M x M), identical on every rank."""
+
+    def __init__(self, model):
+        self.model = model
+
+    @staticmethod
+    def _dS_from_dL(L, gL):
+        """Gradient w.r.t. S = L L^T from the (lower-triangular) gradient w.r.t. L, batched over r."""
+        P = torch.tril(L.transpose(1, 2) @ torch.tril(gL))
+        P = P - 0.5 * torch.diag_embed(torch.diagonal(P, dim1=1, dim2=2))
+        eye = torch.eye(L.shape[-1], dtype=L.dtype, device=L.device).expand_as(L)
+        Linv = torch.linalg.solve_triangular(L, eye, upper=False)
+        return 0.5 * Linv.transpose(1, 2) @ (P + P.transpose(1, 2)) @ Linv
+
+    @torch.no_grad()
+    def step(self, grads, gamma):
+        """grads: per-layer dicts of d ELBO / d(q_mu [M,R], q_sqrt [R,M,M]) (all ranks' sum).  All layers are updated, or none."""
+        new = []
+        for layer, g in zip(self.model.layers, grads):
+            mu = layer.q_mu.T.unsqueeze(2)                                 # [R, M, 1]
+            L = torch.tril(layer.q_sqrt)
+            gq_mu, gq_sqrt = allreduce_sum_(g["q_mu"].clone()), allreduce_sum_(g["q_sqrt"].clone())   # image-sharded: sum over ranks
+            g_mu = -gq_mu.T.unsqueeze(2)                                   # L = -ELBO
+            G = self._dS_from_dL(L, -torch.tril(gq_sqrt))
+            eye = torch.eye(L.shape[-1], dtype=L.dtype, device=L.device).expand_as(L)
+            Linv = torch.linalg.solve_triangular(L, eye, upper=False)
+            Sinv = Linv.transpose(1, 2) @ Linv
+            th1 = Sinv @ mu - gamma * (g_mu - 2.0 * G @ mu)
+            prec = Sinv + 2.0 * gamma * G                                  # -2 theta_2'
+            prec = 0.5 * (prec + prec.transpose(1, 2))
+            Lp, info = torch.linalg.cholesky_ex(prec)
+            if int(info.abs().max().item()) != 0 or not bool(torch.isfinite(Lp).all()):
+                raise _lib.NotPositiveDefiniteError("natural-gradient step with gamma = %g leaves the set of valid covariances "
+                                                    "(cf. experiment.py:45-49)" % gamma)
+            Lpinv = torch.linalg.solve_triangular(Lp, eye, upper=False)
+            S = Lpinv.transpose(1, 2) @ Lpinv
+            Ln, info2 = torch.linalg.cholesky_ex(0.5 * (S + S.transpose(1, 2)))
+            if int(info2.abs().max().item()) != 0:
+                raise _lib.NotPositiveDefiniteError("natural-gradient step: new covariance is not positive definite")
+            new.append(((S @ th1).squeeze(2).T.contiguous(), Ln.contiguous()))
+        for layer, (q_mu, q_sqrt) in zip(self.model.layers, new):
+            layer.q_mu.copy_(q_mu)
+            layer.q_sqrt.copy_(q_sqrt)
+            layer._fresh = False
 
 
 class TrainStep(object):
@@ -516,6 +583,8 @@ class TrainStep(object):
         self.opt.bind()
         self.use_graphs = use_graphs
         self.early_static = os.environ.get("DCGP_EARLY_STATIC", "1") != "0"   # diagnostic switch
+        # SMs the deferred (parameter-only) GEMMs leave to the chains running underneath them (dcgp_set_reserved_sms)
+        self.reserve_sms = int(os.environ.get("DCGP_RESERVE_SMS", "0"))
         self._graphs = {"static": {}, "dynamic": {}}
         self._calls = {"static": {}, "dynamic": {}}
         self._static = {}
@@ -622,9 +691,15 @@ class TrainStep(object):
                 g_mean, g_var = eg._sample_backward(i, gX, zs)
         self._chain(0, wsize, with_elbo=sharded)
         # parameter-only remainder of the upper layers, each followed by its own chain
-        for i in range(1, nl):
-            eg.bwd[i].t_sized_rest()
-            self._chain(i, wsize)
+        if self.reserve_sms:
+            _lib.lib.dcgp_set_reserved_sms(self.reserve_sms)
+        try:
+            for i in range(1, nl):
+                eg.bwd[i].t_sized_rest()
+                self._chain(i, wsize)
+        finally:
+            if self.reserve_sms:
+                _lib.lib.dcgp_set_reserved_sms(0)
         if sharded:
             main.wait_event(self._elbo_ready)      # the returned scalar is complete in main-stream order
         return elbo

@@ -24,6 +24,38 @@ class Zero(object):
         return 0.0
 
 
+class Conv2dMean(object):
+    """conv_gp/mean_functions.py:28-41 (Conv2dMean over IdentityConv2dMean :6-26): a FIXED (non-trainable, models.py:100)
+    VALID convolution whose only non-zero tap is filter[f//2, f//2, 0, 0] = 1 -- output map 0 copies the centre pixel of
+    input map 0 of every patch, the other maps have zero mean; flattened to [N, P*R] (p-major, r fastest: the layer's
+    output layout, layers.py:128-134).  A strided slice, no arithmetic."""
+
+    def __init__(self, filter_size, feature_maps_in, feature_maps_out=1, stride=1):
+        self.filter_size, self.feature_maps_in = int(filter_size), int(feature_maps_in)
+        self.feature_maps_out, self.stride = int(feature_maps_out), int(stride)
+
+    def _taps(self, H, W):
+        f, s = self.filter_size, self.stride
+        OH, OW = (H - f) // s + 1, (W - f) // s + 1
+        c = f // 2
+        return slice(c, c + (OH - 1) * s + 1, s), slice(c, c + (OW - 1) * s + 1, s), OH, OW
+
+    def __call__(self, NHWC_X):
+        N, H, W, _ = NHWC_X.shape
+        ys, xs, OH, OW = self._taps(H, W)
+        out = torch.zeros((N, OH * OW, self.feature_maps_out), dtype=NHWC_X.dtype, device=NHWC_X.device)
+        out[:, :, 0] = NHWC_X[:, ys, xs, 0].reshape(N, OH * OW)
+        return out.reshape(N, OH * OW * self.feature_maps_out)
+
+    def backward(self, g_out, H, W):
+        """d/dX of sum(g_out * self(X)): [N, P*R] -> [N, H*W*C] (zeros except the tapped pixels of input map 0)."""
+        N = g_out.shape[0]
+        ys, xs, OH, OW = self._taps(H, W)
+        gX = torch.zeros((N, H, W, self.feature_maps_in), dtype=g_out.dtype, device=g_out.device)
+        gX[:, ys, xs, 0] = g_out.reshape(N, OH * OW, self.feature_maps_out)[:, :, 0].reshape(N, OH, OW)
+        return gX.reshape(N, H * W * self.feature_maps_in)
+
+
 class TiledInput(object):
     """`tile(X[None], [S,1,1])` of DS/dgp.py:63 without materialising the S identical copies."""
 
@@ -235,7 +267,15 @@ class _PatchGPLayer(Layer):
         _lib.check(_lib.lib.dcgp_layer_apply(d, _lib.ptr(self._prep), _lib.ptr(w), _lib.ptr(X), n_rows, n_rep,
                                              _lib.ptr(z), self._algo(), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(sample),
                                              _lib.ptr(ws), ws.numel(), _lib.stream()))
+        mf = self._mean_function_value(X, n_rep)
+        if mf is not None:                      # layers.py:133-134; the sample is linear in the mean (DS/utils.py:41)
+            mean += mf
+            if sample is not None:
+                sample += mf
         return (mean, var) if z is None else (mean, var, sample)
+
+    def _mean_function_value(self, X, n_rep):
+        return None
 
     def conditional_ND(self, ND_X, full_cov=False):
         if full_cov:
@@ -259,8 +299,8 @@ class ConvLayer(_PatchGPLayer):
 
     def __init__(self, base_kernel, mean_function=None, feature=None, view=None, white=False, gp_count=1, q_mu=None,
                  q_sqrt=None, device=None, **kwargs):
-        if mean_function is not None and not isinstance(mean_function, Zero):
-            raise NotImplementedError("only the default Zero mean (models.py:99) is on the hot path (--identity-mean is off)")
+        if mean_function is not None and not isinstance(mean_function, (Zero, Conv2dMean)):
+            raise NotImplementedError("mean functions of the conv path: Zero (models.py:99) or Conv2dMean (--identity-mean)")
         self.base_kernel = base_kernel
         self.view = view
         self.feature_maps_in = view.feature_maps
@@ -283,6 +323,13 @@ class ConvLayer(_PatchGPLayer):
 
     def _Z_prior(self):
         return None if self.white else _lib.f64(self.Z_prior, self.device)
+
+    def _mean_function_value(self, X, n_rep):
+        if not isinstance(self.mean_function, Conv2dMean):
+            return None
+        v = self._view
+        mf = self.mean_function(X.reshape(X.shape[0], int(v.input_size[0]), int(v.input_size[1]), v.feature_maps))
+        return mf.repeat(n_rep, 1) if n_rep > 1 else mf
 
 
 class SVGP_Layer(_PatchGPLayer):

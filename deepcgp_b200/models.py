@@ -3,8 +3,8 @@
 conv_gp/experiment.py:56-64 (.npy parameter dump).  SURVEY.md 8 row f3: runs once, on the host; the layers it builds
 are the CUDA-backed ones of this package.
 
-The flags object is the reference's argparse namespace (conv_gp/arguments.py:9-43); only the default path is built:
-RBF base kernels, `--last-kernel conv`, Zero mean functions (`--identity-mean` off).
+The flags object is the reference's argparse namespace (conv_gp/arguments.py:9-43); built: RBF base kernels,
+`--last-kernel conv`, Zero mean functions or `--identity-mean` (Conv2dMean).
 """
 import argparse
 
@@ -13,7 +13,7 @@ import torch
 
 from .dgp import DGP_Base
 from .kernels import RBF, ConvKernel, PatchInducingFeatures
-from .layers import ConvLayer, SVGP_Layer, Zero
+from .layers import Conv2dMean, ConvLayer, SVGP_Layer, Zero
 from .likelihoods import MultiClass
 from .views import FullView
 
@@ -45,6 +45,8 @@ def default_parser():
     p.add_argument('--white', action='store_true', default=False)
     p.add_argument('--last-kernel', type=str, default='conv')
     p.add_argument('--identity-mean', action='store_true')
+    p.add_argument('--optimizer', type=str, default='Adam')
+    p.add_argument('--gamma', type=float, default=0.001)
     p.add_argument('--load-model', type=str, default=None)
     return p
 
@@ -163,8 +165,6 @@ class ModelBuilder(object):
         f = self.flags
         if getattr(f, "base_kernel", "rbf") != "rbf" or getattr(f, "last_kernel", "conv") != "conv":
             raise NotImplementedError("only --base-kernel rbf / --last-kernel conv (the defaults) are on the CUDA path")
-        if getattr(f, "identity_mean", False):
-            raise NotImplementedError("--identity-mean is off by default (arguments.py:40) and not built")
         Ms = parse_ints(f.M)
         feature_maps = parse_ints(f.feature_maps)
         strides = parse_ints(f.strides)
@@ -197,7 +197,11 @@ class ModelBuilder(object):
         kern = RBF(L, variance=float(layer_params.get('base_kernel/variance', 5.0)),
                    lengthscales=float(layer_params.get('base_kernel/lengthscales', 5.0)))       # models.py:113-117
         q_mu, q_sqrt = layer_params.get('q_mu'), layer_params.get('q_sqrt')
-        layer = ConvLayer(base_kernel=kern, mean_function=Zero(), feature=feat, view=view, white=self.flags.white,
+        if getattr(self.flags, "identity_mean", False):                                          # models.py:95-100 (not trainable)
+            conv_mean = Conv2dMean(filter_size, NHWC[3], feature_map, stride=stride)
+        else:
+            conv_mean = Zero()
+        layer = ConvLayer(base_kernel=kern, mean_function=conv_mean, feature=feat, view=view, white=self.flags.white,
                           gp_count=feature_map, q_mu=q_mu, q_sqrt=q_sqrt, device=self.device)
         if q_sqrt is None:
             layer.q_sqrt = (layer.q_sqrt * 1e-5).contiguous()                                    # models.py:136-138

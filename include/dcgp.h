@@ -66,6 +66,9 @@ long long dcgp_launch_count(void);
  * most recent conditional-GEMM (which = 0), Kuf (1), dK+dd GEMM (2) and dQ GEMM (3) kernel; dcgp_kernel_ms() waits for the end event and
  * returns the duration in milliseconds (-1 if none was recorded). */
 void dcgp_set_kernel_timing(int on);
+/* SMs the persistent tensor-core kernels launched from now on leave free (0 = use every SM): lets small latency-critical
+ * kernels on another stream (a layer's chain rule / optimiser update / next-step prepare) advance underneath a long GEMM. */
+void dcgp_set_reserved_sms(int n);
 double dcgp_kernel_ms(int which);
 /* Tensor-pipe flops that launch really issued (split products x the k-blocks not skipped as structurally zero), counted by the
  * launcher: the "executed" figure next to the algorithmic one in bench.py's roofline. */
