@@ -97,7 +97,7 @@ double tc_kernel_flops(int which);   // executed tensor-pipe flops of that launc
 
 // split products per k-step of the three big T-sized GEMM families (1..4, see TcParams::nprod in dcgp_tc.cu)
 struct TcProducts { int cond, dk, dq; };
-constexpr int kDefaultProdCond = 3, kDefaultProdDk = 4, kDefaultProdDq = 3;   // measured: tests/test_gpu_bench_size.py, DESIGN.md 'Precision'
+constexpr int kDefaultProdCond = 3, kDefaultProdDk = 3, kDefaultProdDq = 3;   // measured: tests/test_gpu_bench_size.py, DESIGN.md 'Precision'
 const TcProducts& tc_products();
 void tc_set_products(int cond, int dk, int dq);   // 0 leaves a value unchanged
 

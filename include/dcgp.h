@@ -79,7 +79,7 @@ double dcgp_kernel_tensor_flops(int which);
  * the forward conditional (G_r = C_r^T a, A = a; the first stage a = Lm^-1 k, where cancellation happens, always uses 3),
  * dk = da = sum_r s_r a SP_r (A = a), dq = dS_r = a^T diag(s_r) a -- the large GEMMs of conditionals.py:31-65 and of its
  * derivative.  0 leaves a value unchanged.  Defaults: env DCGP_PROD_COND / DCGP_PROD_DK / DCGP_PROD_DQ, else the library's
- * built-in choice (3, 4, 3); dcgp_get_products reports the values in force. */
+ * built-in choice (3, 3, 3); dcgp_get_products reports the values in force. */
 void dcgp_set_products(int cond, int dk, int dq);
 void dcgp_get_products(int* cond_host, int* dk_host, int* dq_host);
 

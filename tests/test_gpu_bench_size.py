@@ -86,14 +86,15 @@ def test_bench_model_forward_elbo_gradients_vs_oracle(cfg_name, N, S):
         assert any(frag in n for n in names), (frag, sorted(n for n in names if "dcgp" in n)[:40])
 
 
-@pytest.mark.parametrize("prods,fwd_tol,grad_tol", [((3, 4, 3), 1e-4, 1e-3), ((3, 3, 3), 1e-4, 1e-3), ((1, 3, 3), 4e-4, 1e-3),
+@pytest.mark.parametrize("prods,fwd_tol,grad_tol", [((3, 3, 3), 1e-4, 1e-3), ((3, 4, 3), 1e-4, 3e-3), ((1, 3, 3), 4e-4, 1e-3),
                                                     ((3, 1, 3), 1e-4, 3e-3), ((3, 3, 1), 1e-4, 1e-2), ((1, 1, 1), 4e-4, 1e-2),
                                                     ((4, 3, 3), 2e-4, 1e-3), ((3, 3, 4), 1e-4, 3e-3)])
 def test_split_product_settings(prods, fwd_tol, grad_tol):
-    """dcgp_set_products: the default (3, 4, 3) and the all-22-bit setting (3, 3, 3) must meet the forward gate (1e-4) and the
-    gradient gate (1e-3) on the benchmark model with margin; the cheaper settings stay available as documented trade-offs
-    (precision) and are held to the looser bounds measured for them (a single fp16 product in G_r = C_r^T a costs
-    3e-5 .. 1.2e-4 on the variance; fp16 operands in the dS GEMM cost up to 3e-3 on d/dq_sqrt)."""
+    """dcgp_set_products: the default (3, 3, 3) -- every operand at 22 bits -- must meet the forward gate (1e-4) and the gradient
+    gate (1e-3) on the benchmark model with margin; the cheaper settings stay available as documented trade-offs (DESIGN.md,
+    precision) and are held to the looser bounds measured for them (a single fp16 product in G_r = C_r^T a costs 3e-5 .. 1.2e-4
+    on the variance; fp16 operands in the dS GEMM up to 3e-3 on d/dq_sqrt; an fp16 `a` in the da GEMM is fine on ELBO gradients
+    (2e-4) but reaches 4e-3 on the lengthscale for unstructured upstream gradients: tests/test_gpu_backward_pieces.py)."""
     import deepcgp_b200 as D
     from deepcgp_b200 import _lib
     from oracle import dcgp_oracle_torch as OT
@@ -105,7 +106,7 @@ def test_split_product_settings(prods, fwd_tol, grad_tol):
     ref_elbo, ref_grads = OT.elbo_and_grads(layers, X.astype(np.float64), Y, [z.astype(np.float64) for z in zs],
                                             bench.NUM_DATA, S, keep=keep)
     saved = _lib.products()
-    assert saved == (3, 4, 3)       # the library's built-in default
+    assert saved == (3, 3, 3)       # the library's built-in default
     try:
         _lib.lib.dcgp_set_products(*prods)
         assert _lib.products() == prods
@@ -123,7 +124,7 @@ def test_split_product_settings(prods, fwd_tol, grad_tol):
         assert worst <= fwd_tol, worst
         assert abs(float(elbo.item()) - ref_elbo) <= 1e-3 * abs(ref_elbo)
         assert all(v <= grad_tol for v in rep.values()), rep
-        if prods in ((3, 3, 3), (3, 4, 3)):
+        if prods == (3, 3, 3):
             assert worst <= 2e-5 and all(v <= 5e-4 for v in rep.values()) and not bad, (worst, rep, bad)    # margin on the default
     finally:
         _lib.lib.dcgp_set_products(*saved)

@@ -95,19 +95,33 @@ def test_experiment_driver_other_optimizers(tmp_path, optimizer):
         assert bool(torch.isfinite(l.q_mu).all()) and bool(torch.isfinite(l.q_sqrt).all())
 
 
-def test_natgrad_backoff_shrinks_gamma_and_retries(tmp_path):
-    """experiment.py:38-49: a natural-gradient step that fails (gamma far too large) is retried with gamma * 0.2, up to 5 times."""
+def test_natgrad_backoff_shrinks_gamma_and_retries(tmp_path, monkeypatch):
+    """experiment.py:38-49: a natural-gradient step that fails is retried with gamma * 0.2 (steps_back += 1), at most five times;
+    the failure itself (Cholesky of the new precision) is covered by test_natgrad_raises_when_the_step_leaves_the_cone."""
     import deepcgp_b200 as D
+    from deepcgp_b200 import _lib
+    from deepcgp_b200.grad import NatGrad
     rng = np.random.RandomState(2)
     X = rng.standard_normal((48, 12, 12, 1))
     Y = rng.randint(0, 10, size=(48, 1))
     flags = _flags(tmp_path, optimizer="NatGrad", gamma=1.0)
     flags.test_every = 1
     exp = D.Experiment(flags, X, Y, device=dev())
-    exp.model.num_data = 5e7            # an enormous data term: dL/deta is huge, gamma = 1 overshoots
-    exp.train_step()
-    assert exp.steps_back >= 1 and exp.gamma() < 1.0
+    real_step, seen = NatGrad.step, []
+
+    def step(self, grads, gamma):
+        seen.append(gamma)
+        if gamma > 0.1:              # stands for tf.errors.InvalidArgumentError from the failed Cholesky
+            raise _lib.NotPositiveDefiniteError("step too long")
+        return real_step(self, grads, gamma)
+
+    monkeypatch.setattr(NatGrad, "step", step)
+    e = exp.train_step()
+    assert seen == pytest.approx([1.0, 0.2, 0.04]) and exp.steps_back == 2 and e["global_step"] == 1
     assert all(bool(torch.isfinite(l.q_sqrt).all()) for l in exp.model.layers)
+    monkeypatch.setattr(NatGrad, "step", lambda self, grads, gamma: (_ for _ in ()).throw(_lib.NotPositiveDefiniteError("always")))
+    with pytest.raises(_lib.NotPositiveDefiniteError):
+        exp.train_step()             # five retries, then the error propagates (experiment.py:41-42)
 
 
 def test_conv2dmean_layer_forward_and_input_gradient():
