@@ -56,6 +56,21 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "l"(tmap), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// One [rows x 64] k-block tile of a K-major operand: row-major planes [rows, K] (2-D map, coordinates (kb*64, row)) or
+// k-blocked planes [K/64][rows][64] (3-D map, coordinates (0, row, kb)) -- the layout of the operands that are transposed in the
+// patch index t (a^T, dd^T, patches^T, g_mean^T): a CTA's tile is one contiguous run in HBM instead of 128-byte rows at a
+// stride of 2*Tpad bytes, for the kernels that write them as well as for the TMA that reads them.
+__device__ __forceinline__ void tma_load_kb(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int kb, int row, int blocked) {
+  if (blocked) tma_load_3d(smem_dst, tmap, bar, 0, row, kb);
+  else tma_load_2d(smem_dst, tmap, bar, kb * 64, row);
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
@@ -162,6 +177,7 @@ struct TcParams {
   int nprod;      // split products per k-step: 3 = Al*Bh + Ah*Bl + Ah*Bh (22-bit operands), 2 = Al*Bh + Ah*Bh (A 22 bits, B 11),
                   // 4 = Ah*Bl + Ah*Bh (A 11 bits, B 22), 1 = Ah*Bh (11-bit operands); planes that are not multiplied are not loaded
   int bf16;       // MODE_GEMM: operand planes are bf16 (hi + lo) instead of fp16
+  int kblocked;   // MODE_GEMM: both operands are k-blocked planes [K/64][rows][64] (3-D tensor maps)
   // ---- MODE_COND
   int T;          // valid patch-columns
   int Mp;         // padded inducing points (multiple of 64)
@@ -324,15 +340,15 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
               uint8_t* sb = st + a_planes * Cfg::kStageA;
               if (mean3) {
                 mbar_expect_tx(&full_bar[stage], Cfg::kStageA + Cfg::kStageB);
-                tma_load_2d(st, pass == 0 ? &tmA_lo : &tmA_hi, &full_bar[stage], kb * kBK, arow);
-                tma_load_2d(sb, pass == 1 ? &tmB_lo : &tmB_hi, &full_bar[stage], kb * kBK, brow);
+                tma_load_kb(st, pass == 0 ? &tmA_lo : &tmA_hi, &full_bar[stage], kb, arow, p.kblocked);
+                tma_load_kb(sb, pass == 1 ? &tmB_lo : &tmB_hi, &full_bar[stage], kb, brow, p.kblocked);
               } else {
                 mbar_expect_tx(&full_bar[stage], a_planes * Cfg::kStageA + b_planes * n * (kBK * 2));
-                tma_load_2d(st, &tmA_hi, &full_bar[stage], kb * kBK, arow);
-                if (a_planes == 2) tma_load_2d(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb * kBK, arow);
+                tma_load_kb(st, &tmA_hi, &full_bar[stage], kb, arow, p.kblocked);
+                if (a_planes == 2) tma_load_kb(st + Cfg::kStageA, &tmA_lo, &full_bar[stage], kb, arow, p.kblocked);
                 if (n == BN) {
-                  tma_load_2d(sb, &tmB_hi, &full_bar[stage], kb * kBK, brow);
-                  if (b_planes == 2) tma_load_2d(sb + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb * kBK, brow);
+                  tma_load_kb(sb, &tmB_hi, &full_bar[stage], kb, brow, p.kblocked);
+                  if (b_planes == 2) tma_load_kb(sb + Cfg::kStageB, &tmB_lo, &full_bar[stage], kb, brow, p.kblocked);
                 } else {                                   // partial block: 64-row boxes of the non-zero rows only
                   for (int c = col_off; c < col_off + n; c += 64) {
                     tma_load_2d(sb + c * (kBK * 2), &tmB64_hi, &full_bar[stage], kb * kBK, brow + c);
@@ -584,6 +600,25 @@ static int make_tmap_f16(CUtensorMap* tm, const void* base, uint64_t rows, uint6
   return DCGP_OK;
 }
 
+// k-blocked planes [K/64][rows][64] (2-byte elements), box = [box_rows, 64] of one k-block, SWIZZLE_128B: lands in shared
+// memory exactly like the 2-D box of make_tmap_f16.
+static int make_tmap_f16_blocked(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t kcols, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled unavailable"); return DCGP_ERR_CUDA; }
+  cuuint64_t dims[3] = {64, rows, kcols / 64};
+  cuuint64_t strides[2] = {128, rows * 128};
+  cuuint32_t box[3] = {64, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (k-blocked) failed (%d) rows=%llu k=%llu box=%u", (int)r, (unsigned long long)rows, (unsigned long long)kcols, box_rows); return DCGP_ERR_CUDA; }
+  return DCGP_OK;
+}
+static int make_tmap_kmajor(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t kcols, uint32_t box_rows, int blocked) {
+  return blocked ? make_tmap_f16_blocked(tm, base, rows, kcols, box_rows) : make_tmap_f16(tm, base, rows, kcols, box_rows);
+}
+
 // Optional live kernel timing (bench.py's roofline leg): CUDA events recorded on the launching stream around the
 // conditional-GEMM and Kuf kernels when enabled; dcgp_kernel_ms() synchronises on the end event and returns the duration.
 static int g_timing = 0;
@@ -780,14 +815,15 @@ int tc_gemm(const TcGemm& g, cudaStream_t st) {
   const int BN = (g.n_pad % 256 == 0) ? 256 : (g.n_pad % 128 == 0 ? 128 : 64);
   CUtensorMap tmAh, tmAl, tmBh, tmBl;
   int rc;
-  if ((rc = make_tmap_f16(&tmAh, g.Ah, g.a_rows_total, g.k_pad, kBM))) return rc;
-  if ((rc = make_tmap_f16(&tmAl, g.Al, g.a_rows_total, g.k_pad, kBM))) return rc;
-  if ((rc = make_tmap_f16(&tmBh, g.Bh, g.b_rows_total, g.k_pad, BN))) return rc;
-  if ((rc = make_tmap_f16(&tmBl, g.Bl, g.b_rows_total, g.k_pad, BN))) return rc;
+  if ((rc = make_tmap_kmajor(&tmAh, g.Ah, g.a_rows_total, g.k_pad, kBM, g.kblocked))) return rc;
+  if ((rc = make_tmap_kmajor(&tmAl, g.Al, g.a_rows_total, g.k_pad, kBM, g.kblocked))) return rc;
+  if ((rc = make_tmap_kmajor(&tmBh, g.Bh, g.b_rows_total, g.k_pad, BN, g.kblocked))) return rc;
+  if ((rc = make_tmap_kmajor(&tmBl, g.Bl, g.b_rows_total, g.k_pad, BN, g.kblocked))) return rc;
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.nkb = g.k_pad / kBK;
   p.bf16 = g.bf16;
+  p.kblocked = g.kblocked;
   p.m_tiles = ceil_div(g.m_pad, kBM); p.n_tiles = g.n_pad / BN;   // a 128-row box may run past a batch / the tensor: extra rows are discarded
   p.splits = g.splits > 1 ? g.splits : 1;
   p.nkb_split = ceil_div(p.nkb, p.splits);
@@ -875,11 +911,57 @@ __global__ void set_scale_kernel(float bound, float* __restrict__ scal2) {
   scal2[0] = s;
   scal2[1] = 1.f / s;
 }
+// scale pair of a plane set from the running maximum of its source (largest entry -> [2^13, 2^14)); the kernel that packs
+// the planes computes it itself from the maximum (no separate launch) and publishes {scale, 1/scale} for the GEMM epilogues
+__device__ __forceinline__ float scale_from_max(float m) {
+  int e = 0;
+  if (m > 0.f && isfinite(m)) frexpf(m, &e);
+  return ldexpf(1.f, 14 - e);
+}
+__device__ __forceinline__ float pack_scale(const float* __restrict__ mx, float* __restrict__ scal2) {
+  if (!mx) return scal2[0];
+  const float s = scale_from_max(mx[0]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scal2[0] = s; scal2[1] = 1.f / s; }
+  return s;
+}
+// Several max|x| scans in ONE launch (blockIdx.y = job): out[job] = max(out[job], max |a|) like maxabs_f64 / maxabs_f32.
+struct MaxJob { const void* p; int f64; long long rows; int cols, ld, lower_period; float* out; };
+struct MaxJobs { MaxJob j[4]; };
+__global__ void __launch_bounds__(256) maxabs_jobs_kernel(MaxJobs J) {
+  const MaxJob job = J.j[blockIdx.y];
+  float m = 0.f;
+  const long long n = job.rows * job.cols;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += 256LL * gridDim.x) {
+    const long long r = e / job.cols;
+    const int c = (int)(e % job.cols);
+    if (job.lower_period > 0 && c > (int)(r % job.lower_period)) continue;
+    m = fmaxf(m, job.f64 ? (float)fabs(((const double*)job.p)[r * job.ld + c]) : fabsf(((const float*)job.p)[r * job.ld + c]));
+  }
+  m = block_max_256(m);
+  if (threadIdx.x == 0) atomic_max_nonneg(job.out, m);
+}
+static MaxJob max_f64(const double* a, long long rows, int cols, int ld, int lower_period, float* out) {
+  MaxJob j; j.p = a; j.f64 = 1; j.rows = rows; j.cols = cols; j.ld = ld; j.lower_period = lower_period; j.out = out; return j;
+}
+static MaxJob max_f32(const float* a, long long n, float* out) {      // a flat array: n rows of one column
+  MaxJob j; j.p = a; j.f64 = 0; j.rows = n; j.cols = 1; j.ld = 1; j.lower_period = 0; j.out = out; return j;
+}
+static int maxabs_jobs(const MaxJob* jobs, int n, cudaStream_t st);
+
 static int grid_for(long long n, int per_block) {
   long long b = (n + per_block - 1) / per_block;
   if (b < 1) b = 1;
   if (b > 148 * 4) b = 148 * 4;
   return (int)b;
+}
+static int maxabs_jobs(const MaxJob* jobs, int n, cudaStream_t st) {
+  if (n < 1 || n > 4) { set_error("maxabs_jobs: 1..4 jobs"); return DCGP_ERR_ARG; }
+  MaxJobs J;
+  long long most = 0;
+  for (int i = 0; i < n; ++i) { J.j[i] = jobs[i]; const long long e = jobs[i].rows * jobs[i].cols; most = e > most ? e : most; }
+  for (int i = n; i < 4; ++i) J.j[i] = jobs[0];
+  maxabs_jobs_kernel<<<dim3(grid_for(most, 4096), n), 256, 0, st>>>(J);
+  return check_launch("maxabs_jobs");
 }
 static int maxabs_f64(const double* a, long long rows, int cols, int ld, int lower_period, float* mx, cudaStream_t st) {
   maxabs_f64_kernel<<<grid_for(rows * cols, 2048), 256, 0, st>>>(a, rows, cols, ld, lower_period, mx);
@@ -894,9 +976,10 @@ static int maxabs_f32(const float* a, long long n, float* mx, cudaStream_t st) {
 // (or its transpose src[b*bstride + j*ld + i]); `lower` zeroes STORED entries above the diagonal; zero padding elsewhere.
 __global__ void __launch_bounds__(256) pack_planes_f64_kernel(const double* __restrict__ src, int ld, long long bstride, int rows,
                                                               int cols, int transpose, int lower, int batch, int rows_pad,
-                                                              int cols_pad, const float* __restrict__ scal2,
+                                                              int cols_pad, const float* __restrict__ mx,
+                                                              float* __restrict__ scal2,
                                                               __half* __restrict__ Ph, __half* __restrict__ Pl) {
-  const double s = (double)scal2[0];
+  const double s = (double)pack_scale(mx, scal2);
   const long long total = (long long)batch * rows_pad * cols_pad;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
     const int j = (int)(e % cols_pad);
@@ -912,19 +995,20 @@ __global__ void __launch_bounds__(256) pack_planes_f64_kernel(const double* __re
     Pl[e] = __float2half_rn((float)(v - (double)__half2float(hi)));
   }
 }
+// mx != nullptr: the scale is derived from mx[0] here and published in scal2; else scal2 holds it already
 static int pack_planes_f64(const double* src, int ld, long long bstride, int rows, int cols, int transpose, int lower, int batch,
-                           int rows_pad, int cols_pad, const float* scal2, void* Ph, void* Pl, cudaStream_t st) {
+                           int rows_pad, int cols_pad, const float* mx, float* scal2, void* Ph, void* Pl, cudaStream_t st) {
   pack_planes_f64_kernel<<<grid_for((long long)batch * rows_pad * cols_pad, 2048), 256, 0, st>>>(
-      src, ld, bstride, rows, cols, transpose, lower, batch, rows_pad, cols_pad, scal2, (__half*)Ph, (__half*)Pl);
+      src, ld, bstride, rows, cols, transpose, lower, batch, rows_pad, cols_pad, mx, scal2, (__half*)Ph, (__half*)Pl);
   return check_launch("pack_planes_f64");
 }
 
 // fp32 -> split-fp16 planes: dst[b*rows_pad + i, j] = s * src[b*bstride + i*ld + j], zero padding elsewhere
 __global__ void __launch_bounds__(256) pack_planes_f32_kernel(const float* __restrict__ src, int ld, long long bstride, int rows,
                                                               int cols, int batch, int rows_pad, int cols_pad,
-                                                              const float* __restrict__ scal2, __half* __restrict__ Ph,
-                                                              __half* __restrict__ Pl) {
-  const float s = scal2[0];
+                                                              const float* __restrict__ mx, float* __restrict__ scal2,
+                                                              __half* __restrict__ Ph, __half* __restrict__ Pl) {
+  const float s = pack_scale(mx, scal2);
   const long long total = (long long)batch * rows_pad * cols_pad;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
     const int j = (int)(e % cols_pad);
@@ -942,9 +1026,10 @@ __global__ void __launch_bounds__(256) pack_planes_f32_kernel(const float* __res
 // Wr comes either as float64 [R, M, M] (Wr64) or as float32 [R*Mp, Mp] (Wr32, the tensor-core product).
 __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, const double* __restrict__ Wr64,
                                   const float* __restrict__ Wr32, const double* __restrict__ beta, int M, int Mp, int R,
-                                  long long rows_total, const float* __restrict__ scal, __half* __restrict__ Wh,
-                                  __half* __restrict__ Wl) {
-  const double sw = (double)scal[0], swm = (double)scal[2];
+                                  long long rows_total, const float* __restrict__ mx, float* __restrict__ scal,
+                                  __half* __restrict__ Wh, __half* __restrict__ Wl) {
+  // scal[0..1] = scale pair of the W blocks (from mx[0]), scal[2..3] = of the mean rows (from mx[1])
+  const double sw = (double)pack_scale(mx, scal), swm = (double)pack_scale(mx ? mx + 1 : nullptr, scal + 2);
   const long long total = rows_total * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(e % Mp);
@@ -983,7 +1068,7 @@ __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float*
   if (mxq[1] > 0.f && isfinite(mxq[1])) frexpf(mxq[1], &exb);
   const double sb = (double)ldexpf(1.f, 14 - exb);
   if (blockIdx.x == 0 && threadIdx.x == 0) { bscal2[0] = (float)sb; bscal2[1] = (float)(1.0 / sb); }
-  const float mmax = 4.f * mxq[0];
+  const float mmax = 4.f * (Kinv ? mxq[0] : fmaxf(mxq[0], 1.f));     // (the identity in S_r - I)
   int ex = 0;
   if (mmax > 0.f && isfinite(mmax)) frexpf(mmax, &ex);
   const double sc = (double)ldexpf(1.f, 14 - ex);
@@ -1012,17 +1097,20 @@ __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float*
   }
 }
 
-__global__ void split_rows_kernel(const float* __restrict__ Kt, long long T, int Mp, long long Tpad, const float* __restrict__ kscal,
-                                  __half* __restrict__ Kh, __half* __restrict__ Kl) {
-  const float s = kscal[0];
+// kblocked: the output planes are k-blocked [Mp/64][Tpad rows][64] (see tma_load_kb) instead of row-major [Tpad, Mp]
+__global__ void split_rows_kernel(const float* __restrict__ Kt, long long T, int Mp, long long Tpad, const float* __restrict__ mx,
+                                  float* __restrict__ kscal, __half* __restrict__ Kh, __half* __restrict__ Kl, int kblocked = 0) {
+  const float s = pack_scale(mx, kscal);
   const long long total = Tpad * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const long long t = e / Mp;
     const float x = (t < T) ? Kt[e] * s : 0.f;
     __half hi, lo;
     split_f16(x, hi, lo);
-    Kh[e] = hi;
-    Kl[e] = lo;
+    const int c = (int)(e - t * Mp);
+    const long long o = kblocked ? ((long long)(c >> 6) * Tpad + t) * 64 + (c & 63) : e;
+    Kh[o] = hi;
+    Kl[o] = lo;
   }
 }
 
@@ -1068,14 +1156,13 @@ int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int 
   const int ab = a_bstride ? batch : 1, bb = b_bstride ? batch : 1;
   int rc;
   cudaMemsetAsync(w.mx, 0, 4 * sizeof(float), st);
-  if ((rc = maxabs_f32(A, (long long)ab * m * k, w.mx + 0, st))) return rc;
-  if ((rc = maxabs_f32(B, (long long)bb * n * k, w.mx + 1, st))) return rc;
-  scales_from_max_kernel<<<1, 32, 0, st>>>(w.mx, 0, 2, w.scal);
+  const MaxJob jobs[2] = {max_f32(A, (long long)ab * m * k, w.mx + 0), max_f32(B, (long long)bb * n * k, w.mx + 1)};
+  if ((rc = maxabs_jobs(jobs, 2, st))) return rc;
   pack_planes_f32_kernel<<<grid_for((long long)ab * w.m_pad * w.k_pad, 2048), 256, 0, st>>>(A, k, (long long)m * k, m, k, ab, w.m_pad, w.k_pad,
-                                                                                          w.scal + 0, (__half*)w.Ah, (__half*)w.Al);
+                                                                                          w.mx + 0, w.scal + 0, (__half*)w.Ah, (__half*)w.Al);
   pack_planes_f32_kernel<<<grid_for((long long)bb * w.n_pad * w.k_pad, 2048), 256, 0, st>>>(B, k, (long long)n * k, n, k, bb, w.n_pad, w.k_pad,
-                                                                                          w.scal + 2, (__half*)w.Bh, (__half*)w.Bl);
-  if ((rc = check_launch("bgemm_pack", 3))) return rc;
+                                                                                          w.mx + 1, w.scal + 2, (__half*)w.Bh, (__half*)w.Bl);
+  if ((rc = check_launch("bgemm_pack", 2))) return rc;
   TcGemm g;
   memset(&g, 0, sizeof(g));
   g.Ah = w.Ah; g.Al = w.Al; g.a_rows_total = (long long)ab * w.m_pad; g.a_batch_rows = a_bstride ? w.m_pad : 0;
@@ -1128,17 +1215,18 @@ int tc_pack_operands(const TcPrep& t, const double* Linv, int ldl, const double*
                      cudaStream_t st) {
   cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
   int rc;
-  if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 0, st))) return rc;
-  if ((rc = maxabs_f64(Wr, (long long)R * M, M, M, 0, t.mx + 0, st))) return rc;
-  if ((rc = maxabs_f64(beta, M, R, R, 0, t.mx + 1, st))) return rc;
-  scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
-  pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, Wr, nullptr, beta, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
+  const MaxJob jobs[3] = {max_f64(Linv, M, M, ldl, 0, t.mx + 0), max_f64(Wr, (long long)R * M, M, M, 0, t.mx + 0),
+                          max_f64(beta, M, R, R, 0, t.mx + 1)};
+  if ((rc = maxabs_jobs(jobs, 3, st))) return rc;
+  pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, Wr, nullptr, beta, M, Mp, R, (long long)w_rows(Mp, R), t.mx, t.scal,
                                                    (__half*)t.Wh, (__half*)t.Wl);
-  return check_launch("tc_pack_operands", 2);
+  return check_launch("tc_pack_operands");
 }
 
 // Wr32[(r*Mp + j)*Mp + i] = L_r[i, j] (i >= j), 0 elsewhere: C_r^T for the whitened chained conditional
-__global__ void qsqrt_t_f32_kernel(const double* __restrict__ q_sqrt, int M, int Mp, int R, float* __restrict__ out) {
+__global__ void qsqrt_t_f32_kernel(const double* __restrict__ q_sqrt, int M, int Mp, int R, float* __restrict__ out,
+                                   const float* __restrict__ mx_in, float* __restrict__ mx_out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomic_max_nonneg(mx_out, mx_in[0]);   // max|C_r| = max|q_sqrt|
   const long long total = (long long)R * Mp * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e % Mp);
@@ -1149,7 +1237,9 @@ __global__ void qsqrt_t_f32_kernel(const double* __restrict__ q_sqrt, int M, int
 }
 
 // out[(r*Mp + i)*Mp + k] = L_r[i, k] (i >= k), 0 elsewhere: C_r for the whitened parameterisation
-__global__ void qsqrt_f32_kernel(const double* __restrict__ q_sqrt, int M, int Mp, int R, float* __restrict__ out) {
+__global__ void qsqrt_f32_kernel(const double* __restrict__ q_sqrt, int M, int Mp, int R, float* __restrict__ out,
+                                 const float* __restrict__ mx_in, float* __restrict__ mx_out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomic_max_nonneg(mx_out, mx_in[0]);   // max|C_r| = max|q_sqrt|
   const long long total = (long long)R * Mp * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(e % Mp);
@@ -1158,7 +1248,6 @@ __global__ void qsqrt_f32_kernel(const double* __restrict__ q_sqrt, int M, int M
     out[e] = (i < M && k < M && i >= k) ? (float)q_sqrt[((long long)r * M + i) * M + k] : 0.f;
   }
 }
-__global__ void set_max_kernel(float* __restrict__ mx, float v) { mx[0] = fmaxf(mx[0], v); }
 
 // Tensor-core build of the R-batched M-only products (the O(R M^3) part of the step's minibatch-independent work):
 //   W_r = L_r^T G            (G = Kuu^-1 symmetric, or Lm^-1 when whitened)                -> fp32, then the W planes
@@ -1172,17 +1261,23 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
   if (parts & 1) {
     // ---- part 1: what the forward conditional GEMM needs (W planes)
     cudaMemsetAsync(t.mx, 0, 8 * sizeof(float), st);
-    if ((rc = maxabs_f64(q_sqrt, (long long)R * M, M, M, M, t.mx + 2, st))) return rc;
-    if (!chained) { if ((rc = maxabs_f64(G, M, M, ldg, 0, t.mx + 3, st))) return rc; }
-    else if (!g_is_linv) { if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 4, st))) return rc; }
-    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 2, 3, t.scal);
-    check_launch("scales_from_max");
+    const double* mvec = chained ? alpha : beta;
+    {   // every max scan part 1 needs, in one launch (the products' own maxima come out of the GEMM epilogue)
+      MaxJob jobs[4];
+      int nj = 0;
+      jobs[nj++] = max_f64(q_sqrt, (long long)R * M, M, M, M, t.mx + 2);
+      if (!chained) jobs[nj++] = max_f64(G, M, M, ldg, 0, t.mx + 3);
+      else if (!g_is_linv) jobs[nj++] = max_f64(Linv, M, M, ldl, 0, t.mx + 4);
+      jobs[nj++] = max_f64(Linv, M, M, ldl, 0, t.mx + 0);
+      jobs[nj++] = max_f64(mvec, M, R, R, 0, t.mx + 1);
+      if ((rc = maxabs_jobs(jobs, nj, st))) return rc;
+    }
     // QT[r*Mp + i, k] = L_r[k, i]  (transpose of the lower-triangular q_sqrt_r)
-    if ((rc = pack_planes_f64(q_sqrt, M, (long long)M * M, M, M, 1, 1, R, Mp, Mp, t.scal + 4, t.QTh, t.QTl, st))) return rc;
-    if (M != Mp) cudaMemsetAsync(t.Wr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);   // padding must not poison the max scan
+    if ((rc = pack_planes_f64(q_sqrt, M, (long long)M * M, M, M, 1, 1, R, Mp, Mp, t.mx + 2, t.scal + 4, t.QTh, t.QTl, st))) return rc;
+    if (M != Mp) cudaMemsetAsync(t.Wr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
     if (chained && g_is_linv) {
-      // whitened: C_r = L_r, so the stage-2 operand C_r^T is just the transposed q_sqrt
-      qsqrt_t_f32_kernel<<<num_sms() * 8, 256, 0, st>>>(q_sqrt, M, Mp, R, t.Wr32);
+      // whitened: C_r = L_r, so the stage-2 operand C_r^T is just the transposed q_sqrt (its maximum is that of q_sqrt)
+      qsqrt_t_f32_kernel<<<num_sms() * 8, 256, 0, st>>>(q_sqrt, M, Mp, R, t.Wr32, t.mx + 2, t.mx + 0);
       if ((rc = check_launch("qsqrt_t"))) return rc;
     } else {
       TcGemm g;
@@ -1190,39 +1285,39 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
       g.Ah = t.QTh; g.Al = t.QTl; g.a_rows_total = (long long)R * Mp; g.a_batch_rows = Mp;
       if (!chained) {
         // W_r = L_r^T G.  B operand: B[j, k] = G[k, j]  (G symmetric when it is Kuu^-1; the transpose of Lm^-1 when whitened)
-        if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
+        if ((rc = pack_planes_f64(G, ldg, 0, M, M, g_is_linv ? 1 : 0, g_is_linv ? 1 : 0, 1, Mp, Mp, t.mx + 3, t.scal + 6, t.Gh, t.Gl, st))) return rc;
         g.Bh = t.Gh; g.Bl = t.Gl; g.b_scal = t.scal + 6;
       } else {
         // C_r^T = L_r^T Lm^-T:  C[(r,j), i] = sum_k L_r[k, j] Lm^-1[i, k].  B operand: the rows of Lm^-1 (in the Lp planes,
         // which part 2 re-packs with the prior's Lp^-1 afterwards)
-        if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 8, t.Lph, t.Lpl, st))) return rc;
+        if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 0, 1, 1, Mp, Mp, t.mx + 4, t.scal + 8, t.Lph, t.Lpl, st))) return rc;
         g.Bh = t.Lph; g.Bl = t.Lpl; g.b_scal = t.scal + 8;
       }
       g.b_rows_total = Mp; g.b_batch_rows = 0;
       g.batch = R; g.m = M; g.n = M; g.m_pad = Mp; g.n_pad = Mp; g.k_pad = Mp;
       g.a_scal = t.scal + 4;
       g.C = t.Wr32; g.c_batch_stride = (long long)Mp * Mp; g.ldc = Mp;
+      g.absmax_out = t.mx + 0;                  // joins max|Lm^-1| in the W-block slot
       if ((rc = tc_gemm(g, st))) return rc;
     }
     // W planes for the conditional GEMM: block 0 = Lm^-1 (float64), blocks 1..R = W_r or C_r^T (fp32 product), mean rows =
     // beta^T or alpha^T
-    const double* mvec = chained ? alpha : beta;
-    if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 0, st))) return rc;
-    if ((rc = maxabs_f32(t.Wr32, (long long)R * Mp * Mp, t.mx + 0, st))) return rc;
-    if ((rc = maxabs_f64(mvec, M, R, R, 0, t.mx + 1, st))) return rc;
-    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 0, 2, t.scal);
-    pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, mvec, M, Mp, R, (long long)w_rows(Mp, R), t.scal,
+    pack_w_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(Linv, ldl, nullptr, t.Wr32, mvec, M, Mp, R, (long long)w_rows(Mp, R), t.mx, t.scal,
                                                      (__half*)t.Wh, (__half*)t.Wl);
-    if ((rc = check_launch("tc_build_operands", 2))) return rc;
+    if ((rc = check_launch("tc_build_operands"))) return rc;
   }
   if (!(parts & 2)) return DCGP_OK;
   // ---- part 2: KL trace and the backward operands (not needed by the forward conditional)
-  cudaMemsetAsync(t.mx + 3, 0, 2 * sizeof(float), st);   // slots 3 (Lm^-1 planes below) and 4 (prior's Lp^-1)
+  cudaMemsetAsync(t.mx + 3, 0, 5 * sizeof(float), st);   // slots 3 (Lm^-1), 4 (prior's Lp^-1), 5 (S_r), 6 (alpha), 7 (C_r)
+  {
+    MaxJob jobs[3];
+    int nj = 0;
+    if (Lpinv) jobs[nj++] = max_f64(Lpinv, M, M, ldp, 0, t.mx + 4);
+    if (Kinv) { jobs[nj++] = max_f64(Linv, M, M, ldl, 0, t.mx + 3); jobs[nj++] = max_f64(alpha, M, R, R, 0, t.mx + 6); }
+    if (nj && (rc = maxabs_jobs(jobs, nj, st))) return rc;
+  }
   if (Lpinv) {
-    if ((rc = maxabs_f64(Lpinv, M, M, ldp, 0, t.mx + 4, st))) return rc;
-    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 4, 1, t.scal);
-    check_launch("scales_from_max");
-    if ((rc = pack_planes_f64(Lpinv, ldp, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 8, t.Lph, t.Lpl, st))) return rc;
+    if ((rc = pack_planes_f64(Lpinv, ldp, 0, M, M, 0, 1, 1, Mp, Mp, t.mx + 4, t.scal + 8, t.Lph, t.Lpl, st))) return rc;
     cudaMemsetAsync(trace_out, 0, sizeof(double), st);
     TcGemm h;
     memset(&h, 0, sizeof(h));
@@ -1238,14 +1333,12 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
   //      S_r = C_r C_r^T, SP planes [R*Mp + 256, Mp] = 2 (S_r - I), alpha planes, Lm^-T planes.  Br32 keeps C_r for the host's
   //      M-only chain rule.
   {
-    if ((rc = maxabs_f64(Linv, M, M, ldl, 0, t.mx + 3, st))) return rc;      // (slot 3 was zeroed by part 1 / above)
-    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 3, 1, t.scal);
-    if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 0, 1, 1, Mp, Mp, t.scal + 6, t.Gh, t.Gl, st))) return rc;
+    if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 0, 1, 1, Mp, Mp, t.mx + 3, t.scal + 6, t.Gh, t.Gl, st))) return rc;
     cudaMemsetAsync((char*)t.LTh + (size_t)Mp * Mp * 2, 0, (size_t)256 * Mp * 2, st);
     cudaMemsetAsync((char*)t.LTl + (size_t)Mp * Mp * 2, 0, (size_t)256 * Mp * 2, st);
-    if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 1, 1, 1, Mp, Mp, t.scal + 6, t.LTh, t.LTl, st))) return rc;
-    if (g_is_linv) {          // whitened: C_r = L_r
-      qsqrt_f32_kernel<<<num_sms() * 8, 256, 0, st>>>(q_sqrt, M, Mp, R, t.Br32);
+    if ((rc = pack_planes_f64(Linv, ldl, 0, M, M, 1, 1, 1, Mp, Mp, nullptr, t.scal + 6, t.LTh, t.LTl, st))) return rc;
+    if (g_is_linv) {          // whitened: C_r = L_r (its maximum is that of q_sqrt, slot 2 of part 1)
+      qsqrt_f32_kernel<<<num_sms() * 8, 256, 0, st>>>(q_sqrt, M, Mp, R, t.Br32, t.mx + 2, t.mx + 7);
       if ((rc = check_launch("qsqrt_f32"))) return rc;
     } else {
       TcGemm b1;
@@ -1255,13 +1348,12 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
       b1.batch = R; b1.m = M; b1.n = M; b1.m_pad = Mp; b1.n_pad = Mp; b1.k_pad = Mp;
       b1.a_scal = t.scal + 6; b1.b_scal = t.scal + 4;
       b1.C = t.Br32; b1.c_batch_stride = (long long)Mp * Mp; b1.ldc = Mp;
+      b1.absmax_out = t.mx + 7;
       if (M != Mp) cudaMemsetAsync(t.Br32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
       if ((rc = tc_gemm(b1, st))) return rc;
     }
-    if ((rc = maxabs_f32(t.Br32, (long long)R * Mp * Mp, t.mx + 7, st))) return rc;
-    scales_from_max_kernel<<<1, 32, 0, st>>>(t.mx, 7, 1, t.scal);
-    split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(t.Br32, (long long)R * Mp, Mp, (long long)R * Mp, t.scal + 14, (__half*)t.BRh,
-                                                     (__half*)t.BRl);
+    split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(t.Br32, (long long)R * Mp, Mp, (long long)R * Mp, t.mx + 7, t.scal + 14,
+                                                     (__half*)t.BRh, (__half*)t.BRl);
     TcGemm b2;
     memset(&b2, 0, sizeof(b2));
     b2.Ah = t.BRh; b2.Al = t.BRl; b2.a_rows_total = (long long)R * Mp; b2.a_batch_rows = Mp;
@@ -1269,14 +1361,12 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
     b2.batch = R; b2.m = M; b2.n = M; b2.m_pad = Mp; b2.n_pad = Mp; b2.k_pad = Mp;
     b2.a_scal = t.scal + 14; b2.b_scal = t.scal + 14;
     b2.C = t.Qr32; b2.c_batch_stride = (long long)Mp * Mp; b2.ldc = Mp;     // S_r; Br32 keeps C_r for the M-only chain rule
+    b2.absmax_out = t.mx + 5;
     if (M != Mp) cudaMemsetAsync(t.Qr32, 0, (size_t)R * Mp * Mp * sizeof(float), st);
     if ((rc = tc_gemm(b2, st))) return rc;
-    if ((rc = maxabs_f32(t.Qr32, (long long)R * Mp * Mp, t.mx + 5, st))) return rc;
-    set_max_kernel<<<1, 1, 0, st>>>(t.mx + 5, 1.f);                         // the identity in S_r - I
-    if ((rc = maxabs_f64(alpha, M, R, R, 0, t.mx + 6, st))) return rc;
     pack_qp_f16_kernel<<<num_sms() * 8, 256, 0, st>>>(nullptr, t.Qr32, alpha, M, Mp, R, t.mx + 5, t.scal + 10, (__half*)t.QBh, (__half*)t.QBl,
                                                       t.beta32, t.scal + 16, (__half*)t.BTh, (__half*)t.BTl);
-    if ((rc = check_launch("tc_build_backward_operands", 4))) return rc;
+    if ((rc = check_launch("tc_build_backward_operands", 2))) return rc;
   }
   return DCGP_OK;
 }
@@ -1612,9 +1702,8 @@ void tc_carve_cond(TcCondWork& w, int M, int Mp, int R, size_t T, void* buf) {
 int tc_split_rows(const float* Kt, int T, int Mp, const TcCondWork& w, cudaStream_t st) {
   cudaMemsetAsync(w.kscal + 4, 0, sizeof(float), st);
   maxabs_f32_kernel<<<grid_for((long long)T * Mp, 4096), 256, 0, st>>>(Kt, (long long)T * Mp, w.kscal + 4);
-  scales_from_max_kernel<<<1, 32, 0, st>>>(w.kscal + 4, 0, 1, w.kscal);
-  split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(Kt, T, Mp, (long long)w.Tpad, w.kscal, (__half*)w.Kh, (__half*)w.Kl);
-  return check_launch("tc_split_rows", 3);
+  split_rows_kernel<<<num_sms() * 8, 256, 0, st>>>(Kt, T, Mp, (long long)w.Tpad, w.kscal + 4, w.kscal, (__half*)w.Kh, (__half*)w.Kl);
+  return check_launch("tc_split_rows", 2);
 }
 
 void tc_carve_apply(TcApplyWork& a, int kind, int M, int Mp, int R, int L, size_t Tk, size_t T, void* buf) {

@@ -71,6 +71,7 @@ struct TcGemm {
   int bf16;                                      // planes are bf16 hi/lo (unscaled values allowed) instead of fp16
   int splits; long long c_split_stride;          // split-K: partial C per split (caller reduces); splits <= 1 = off
   int nprod;                                     // split products per k-step (0 = 3)
+  int kblocked;                                  // both operands are k-blocked planes [k_pad/64][rows][64] instead of row-major [rows, k_pad]
 };
 size_t tc_bgemm_workspace_bytes(int batch, int m, int n, int k);
 int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride, long long b_bstride,

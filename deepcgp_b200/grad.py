@@ -1,10 +1,9 @@
 """ELBO gradient and optimiser step: the reference gets gradients from TensorFlow autodiff inside
 GPflow's AdamOptimizer (conv_gp/experiment.py:84-108); here the minibatch-sized backward runs in libdcgp.so
-(dcgp_layer_backward: four split-fp16 tcgen05 GEMMs per layer + elementwise kernels) and the small minibatch-independent
-chain rule (Q_blk, beta, KL -> Z, kernel hyper-parameters, q_mu, q_sqrt) is dense float64 algebra on the device.
-
-NOTE (round 1): that M-only chain rule is evaluated with torch.autograd over torch.linalg ops (cuSOLVER/cuBLAS, float64);
-it is O(R M^3), independent of the batch, and is the one place on the step where library kernels are used.
+(dcgp_layer_backward: split-fp16 tcgen05 GEMMs per layer + elementwise kernels) and the small minibatch-independent
+chain rule (dS_r, dalpha, KL -> Z, kernel hyper-parameters, q_mu, q_sqrt) is a closed form in dense algebra on the device:
+its R-batched M^3 products on the library's own tensor-core GEMM (dcgp_bgemm_nt), the single-matrix float64 products as
+torch ops (cuBLAS; O(M^3), independent of the batch -- the one place on the step where library kernels are used).
 """
 import math
 import os
