@@ -688,8 +688,10 @@ static int num_sms() {
 // prepare under the parameter-only GEMMs of the layers above) sets it around those launches: CTAs of a persistent kernel
 // never yield, so without free SMs the other stream only advances in the gaps between kernels.
 static int g_reserve_sms = 0;
-void tc_set_reserved_sms(int n) { g_reserve_sms = n < 0 ? 0 : n; }
-static int grid_sms() { const int n = num_sms() - g_reserve_sms; return n < 1 ? 1 : n; }
+void tc_set_reserved_sms(int n) { g_reserve_sms = n; }
+// n < 0: one CTA per work item instead of a persistent grid -- CTAs retire continuously, so a higher-priority stream gets SMs
+// at every CTA boundary (a few microseconds apart) without any SM being taken away from this kernel for good.
+static int grid_sms() { if (g_reserve_sms < 0) return 1 << 30; const int n = num_sms() - g_reserve_sms; return n < 1 ? 1 : n; }
 
 constexpr int kWPadRows = 256;   // zero rows after the mean block so a BN-row box never leaves the tensor
 

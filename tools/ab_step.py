@@ -1,6 +1,6 @@
 """A/B timing of TrainStep settings inside ONE process (run-to-run variance between gpurun boxes is +-0.5 ms):
 alternates the settings in blocks of `--block` steps, `--rounds` times, L2 flushed between steps.
-    python tools/ab_step.py reserve 0 16 32        (DCGP_RESERVE_SMS values)"""
+    python tools/ab_step.py reserve 0 16 32 -1      (DCGP_RESERVE_SMS values; -1 = one CTA per item for the deferred GEMMs)"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
