@@ -65,6 +65,8 @@ SIGNATURES = {
     "dcgp_backward_workspace_bytes": (_sz, [_pd, _i, _i]),
     "dcgp_layer_backward": (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dcgp_layer_backward_phases": (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
+    "dcgp_chain_rule_workspace_bytes": (_sz, [_pd]),
+    "dcgp_layer_chain_rule": (_i, [_pd, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dcgp_bgemm_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "dcgp_bgemm_nt": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, C.c_longlong, C.c_longlong, _vp, _sz, _vp]),
     "dcgp_multiclass_varexp_grad": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp]),

@@ -590,6 +590,31 @@ int dcgp_layer_backward(const dcgp_layer_desc* d, const void* prep_buf, const vo
                                     gw, ws, ws_bytes, 3, stream);
 }
 
+size_t dcgp_chain_rule_workspace_bytes(const dcgp_layer_desc* d) {
+  if (check_desc(d)) return 0;
+  return chain_rule_workspace_bytes(d->M, d->R, d->f * d->f * d->C) + 256;
+}
+
+int dcgp_layer_chain_rule(const dcgp_layer_desc* d, const void* prep_buf, const void* prepare_ws, const double* Z,
+                          const double* Z_prior, const double* q_mu, const double* q_sqrt, const double* hyp, const double* gQB,
+                          const double* gZ_direct, const double* gscal, double kl_weight, int parts, double* gZ, double* ghyp,
+                          double* g_qmu, double* g_qsqrt, void* ws, size_t ws_bytes, void* stream) {
+  DCGP_TRY(check_desc(d));
+  if (!prep_buf || !prepare_ws || !Z || !q_mu || !q_sqrt || parts < 1 || parts > 3) { set_error("chain_rule: bad argument"); return DCGP_ERR_ARG; }
+  if ((parts & 2) && (!gQB || !gZ_direct || !gscal || !gZ || !ghyp || !g_qmu || !g_qsqrt)) { set_error("chain_rule: null gradient buffer"); return DCGP_ERR_ARG; }
+  if (!ws || ws_bytes < dcgp_chain_rule_workspace_bytes(d)) { set_error("chain_rule: workspace too small"); return DCGP_ERR_WORKSPACE; }
+  F64Work w = carve_f64(d->M, d->R, const_cast<void*>(prepare_ws));
+  Prep p = carve_prep(d, const_cast<void*>(prep_buf));
+  ChainInputs in;
+  in.Kinv = w.Kinv; in.Li = w.Linv; in.Lpinv = w.Lpinv; in.Lm = w.Kuu; in.alpha = w.alpha; in.ldi = w.Mq;
+  in.C32 = p.tc.Br32; in.S32 = p.tc.Qr32; in.Ct32 = p.tc.Wr32;
+  // (a ConvLayer whose KL prior is the current Z shares the factor of Kuu: Lp^-1 = Lm^-1)
+  const bool own_prior = (d->kind == DCGP_LAYER_CONV) && Z_prior && Z_prior != Z && !d->white;
+  if (!own_prior) in.Lpinv = w.Linv;
+  return chain_rule(d, in, Z, own_prior ? Z_prior : nullptr, q_mu, q_sqrt, hyp, gQB, gZ_direct, gscal, kl_weight, parts, gZ, ghyp,
+                    g_qmu, g_qsqrt, (void*)align_up((size_t)ws, 256), (cudaStream_t)stream);
+}
+
 size_t dcgp_bgemm_workspace_bytes(int batch, int m, int n, int k) {
   if (batch < 1 || m < 1 || n < 1 || k < 1) return 0;
   return tc_bgemm_workspace_bytes(batch, m, n, k);

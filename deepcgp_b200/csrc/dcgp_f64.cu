@@ -58,6 +58,16 @@ __device__ __forceinline__ void gemm_f64_fetch(const GemmF64& g, const double* _
   }
 }
 
+// D (8x8) += A (8x4, row) * B (4x8, col) on the float64 tensor cores.  Fragments (PTX ISA, mma.m8n8k4 .f64):
+//   a: row = lane / 4, col = lane % 4;   b: row (k) = lane % 4, col (n) = lane / 4;   c0, c1: row = lane / 4, cols 2 (lane % 4) + {0, 1}
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// 64x64 output tile per CTA, 16-deep k-slices staged through shared memory (register double buffering of the global loads:
+// these GEMMs are small and latency-bound), inner product on DMMA: 8 warps as 4 (m) x 2 (n), each 16 x 32 = 2 x 4 m8n8 tiles.
 __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
   __shared__ double As[16][64 + 2];
   __shared__ double Bs[16][64 + 2];
@@ -66,12 +76,14 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
   const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
   const double* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
   double* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;       // this warp's 16 x 32 sub-tile
+  const int fr = lane >> 2, fc = lane & 3;
+  double acc[2][4][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
 
   // k-range that can be non-zero given triangular operands (block-uniform)
   int kbeg = 0, kend = g.k;
@@ -90,30 +102,34 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
     __syncthreads();
     if (k0 + 16 < kend) gemm_f64_fetch(g, A, B, i0, j0, k0 + 16, tid, ra, rb);
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      double a[4], b[4];
+    for (int kk = 0; kk < 16; kk += 4) {
+      double a[2], b[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; b[u] = Bs[kk][tx * 4 + u]; }
+      for (int u = 0; u < 2; ++u) a[u] = As[kk + fc][wm + u * 8 + fr];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int v = 0; v < 4; ++v) b[v] = Bs[kk + fc][wn + v * 8 + fr];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) dmma_884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int gi = i0 + ty * 4 + u;
+  for (int u = 0; u < 2; ++u) {
+    const int gi = i0 + wm + u * 8 + fr;
     if (gi >= g.m) continue;
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int gj = j0 + tx * 4 + v;
-      if (gj >= g.n) continue;
-      double* p = C + (long long)gi * g.ldc + gj;
-      double r = g.alpha * acc[u][v];
-      if (g.beta != 0.0) r += g.beta * (*p);
-      *p = r;
-    }
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int gj = j0 + wn + v * 8 + 2 * fc + e;
+        if (gj >= g.n) continue;
+        double* p = C + (long long)gi * g.ldc + gj;
+        double r = g.alpha * acc[u][v][e];
+        if (g.beta != 0.0) r += g.beta * (*p);
+        *p = r;
+      }
   }
 }
 

@@ -1152,17 +1152,23 @@ static BgemmWork carve_bgemm(int batch, int m, int n, int k, void* buf) {
 }
 size_t tc_bgemm_workspace_bytes(int batch, int m, int n, int k) { return carve_bgemm(batch, m, n, k, nullptr).bytes + 1024; }
 
-int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride, long long b_bstride,
-                void* ws, cudaStream_t st) {
+int tc_bgemm_nt_ld(const float* A, int lda, long long a_bstride, const float* B, int ldb, long long b_bstride, float* C, int ldc,
+                   long long c_bstride, int batch, int m, int n, int k, void* ws, cudaStream_t st) {
   BgemmWork w = carve_bgemm(batch, m, n, k, (void*)align_up((size_t)ws, 1024));
   const int ab = a_bstride ? batch : 1, bb = b_bstride ? batch : 1;
   int rc;
   cudaMemsetAsync(w.mx, 0, 4 * sizeof(float), st);
-  const MaxJob jobs[2] = {max_f32(A, (long long)ab * m * k, w.mx + 0), max_f32(B, (long long)bb * n * k, w.mx + 1)};
+  MaxJob jobs[2];
+  jobs[0].p = A; jobs[0].f64 = 0; jobs[0].rows = (long long)(ab - 1) * (a_bstride / (lda > 0 ? lda : 1)) + m; jobs[0].cols = k; jobs[0].ld = lda;
+  jobs[0].lower_period = 0; jobs[0].out = w.mx + 0;
+  jobs[1].p = B; jobs[1].f64 = 0; jobs[1].rows = (long long)(bb - 1) * (b_bstride / (ldb > 0 ? ldb : 1)) + n; jobs[1].cols = k; jobs[1].ld = ldb;
+  jobs[1].lower_period = 0; jobs[1].out = w.mx + 1;
+  if (ab > 1 && a_bstride % lda) { set_error("bgemm: batch stride of A must be a multiple of its leading dimension"); return DCGP_ERR_ARG; }
+  if (bb > 1 && b_bstride % ldb) { set_error("bgemm: batch stride of B must be a multiple of its leading dimension"); return DCGP_ERR_ARG; }
   if ((rc = maxabs_jobs(jobs, 2, st))) return rc;
-  pack_planes_f32_kernel<<<grid_for((long long)ab * w.m_pad * w.k_pad, 2048), 256, 0, st>>>(A, k, (long long)m * k, m, k, ab, w.m_pad, w.k_pad,
+  pack_planes_f32_kernel<<<grid_for((long long)ab * w.m_pad * w.k_pad, 2048), 256, 0, st>>>(A, lda, a_bstride, m, k, ab, w.m_pad, w.k_pad,
                                                                                           w.mx + 0, w.scal + 0, (__half*)w.Ah, (__half*)w.Al);
-  pack_planes_f32_kernel<<<grid_for((long long)bb * w.n_pad * w.k_pad, 2048), 256, 0, st>>>(B, k, (long long)n * k, n, k, bb, w.n_pad, w.k_pad,
+  pack_planes_f32_kernel<<<grid_for((long long)bb * w.n_pad * w.k_pad, 2048), 256, 0, st>>>(B, ldb, b_bstride, n, k, bb, w.n_pad, w.k_pad,
                                                                                           w.mx + 1, w.scal + 2, (__half*)w.Bh, (__half*)w.Bl);
   if ((rc = check_launch("bgemm_pack", 2))) return rc;
   TcGemm g;
@@ -1171,8 +1177,13 @@ int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int 
   g.Bh = w.Bh; g.Bl = w.Bl; g.b_rows_total = (long long)bb * w.n_pad; g.b_batch_rows = b_bstride ? w.n_pad : 0;
   g.batch = batch; g.m = m; g.n = n; g.m_pad = w.m_pad; g.n_pad = w.n_pad; g.k_pad = w.k_pad;
   g.a_scal = w.scal + 0; g.b_scal = w.scal + 2;
-  g.C = C; g.c_batch_stride = (long long)m * n; g.ldc = n;
+  g.C = C; g.c_batch_stride = c_bstride; g.ldc = ldc;
   return tc_gemm(g, st);
+}
+
+int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride, long long b_bstride,
+                void* ws, cudaStream_t st) {
+  return tc_bgemm_nt_ld(A, k, a_bstride, B, k, b_bstride, C, n, (long long)m * n, batch, m, n, k, ws, st);
 }
 
 

@@ -76,6 +76,9 @@ struct TcGemm {
 size_t tc_bgemm_workspace_bytes(int batch, int m, int n, int k);
 int tc_bgemm_nt(const float* A, const float* B, float* C, int batch, int m, int n, int k, long long a_bstride, long long b_bstride,
                 void* ws, cudaStream_t st);
+// the same with explicit leading dimensions / batch strides (in elements; strides multiples of the leading dimension; ldc % 4 == 0)
+int tc_bgemm_nt_ld(const float* A, int lda, long long a_bstride, const float* B, int ldb, long long b_bstride, float* C, int ldc,
+                   long long c_bstride, int batch, int m, int n, int k, void* ws, cudaStream_t st);
 int tc_gemm_splits(const TcGemm& g);             // number of splits tc_gemm will really use
 int tc_gemm(const TcGemm& g, cudaStream_t st);
 
@@ -116,5 +119,17 @@ void tc_carve_bwd(TcBwdWork& b, int kind, int M, int Mp, int R, int L, size_t Tk
 int tc_layer_backward(const dcgp_layer_desc* d, const View& v, const TcPrep& prep, const TcApplyWork& a, const TcBwdWork& b,
                       const double* Z, const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
                       const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw, int phases, cudaStream_t st);
+
+// ---- dcgp_chain.cu: the M-only chain rule of one layer (native counterpart of what tf.gradients derives for the minibatch-
+// independent part of the layer; see the file header)
+struct ChainInputs {
+  const double *Kinv, *Li, *Lpinv, *Lm, *alpha;   // Kinv ld M; Li, Lpinv ld ldi; Lm ld M (lower); alpha [M,R] (non-whitened)
+  int ldi;
+  const float *C32, *S32, *Ct32;                  // [R,Mp,Mp]: C_r, S_r, C_r^T
+};
+size_t chain_rule_workspace_bytes(int M, int R, int L);
+int chain_rule(const dcgp_layer_desc* d, const ChainInputs& in, const double* Z, const double* Z_prior, const double* q_mu,
+               const double* q_sqrt, const double* hyp_dev, const double* gQB, const double* gZ_direct, const double* gscal,
+               double kl_weight, int parts, double* gZ, double* ghyp, double* g_qmu, double* g_qsqrt, void* ws, cudaStream_t st);
 
 }  // namespace dcgp

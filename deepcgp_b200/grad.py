@@ -33,8 +33,9 @@ def softplus_inv(x):
 class LayerBackward(object):
     """Per-layer buffers + the M-only chain rule."""
 
-    BATCHED_DTYPE = torch.float32     # dtype of the R-batched M^3 products of the chain rule (torch.float64 = all-double)
-    TC_BATCHED = True                 # float32 batched products on the library's split-fp16 tcgen05 GEMM (dcgp_bgemm_nt)
+    NATIVE = True                     # M-only chain rule in libdcgp.so (dcgp_layer_chain_rule); False: the torch restatement
+    BATCHED_DTYPE = torch.float32     # (torch restatement) dtype of the R-batched M^3 products (torch.float64 = all-double)
+    TC_BATCHED = True                 # (torch restatement) batched products on the library's tcgen05 GEMM (dcgp_bgemm_nt)
 
     def __init__(self, layer):
         self.layer = layer
@@ -101,6 +102,52 @@ class LayerBackward(object):
         gZ = -(Hs.sum(1, keepdim=True) * Z - Hs @ Z) / (ls * ls)
         return gvar, gls, gZ
 
+    # ---- native chain rule (dcgp_layer_chain_rule): the product path
+    def _chain(self, parts, kl_weight, hyp):
+        layer = self.layer
+        dev = layer.device
+        d = layer._desc()
+        M, R, L = self.M, self.R, self.L
+        if getattr(self, "_chain_out", None) is None:
+            self._chain_out = (torch.zeros((M, L), dtype=torch.float64, device=dev), torch.zeros(2, dtype=torch.float64, device=dev),
+                               torch.zeros((M, R), dtype=torch.float64, device=dev),
+                               torch.zeros((R, M, M), dtype=torch.float64, device=dev))
+        gZ, ghyp, gqmu, gqsqrt = self._chain_out
+        ws = self.ws.get("chain", _lib.lib.dcgp_chain_rule_workspace_bytes(d), dev)
+        prep_ws = layer._ws.get("prep", 0, dev)
+        Z = _lib.f64(layer.feature.Z, dev)
+        Zp = layer._Z_prior()
+        self._chain_keep = (Z, Zp, hyp)
+        _lib.check(_lib.lib.dcgp_layer_chain_rule(
+            d, _lib.ptr(layer._prep), _lib.ptr(prep_ws), _lib.ptr(Z), _lib.ptr(Zp), _lib.ptr(_lib.f64(layer.q_mu, dev)),
+            _lib.ptr(_lib.f64(layer.q_sqrt, dev)), _lib.ptr(hyp), _lib.ptr(self.gQB), _lib.ptr(self.gZ), _lib.ptr(self.gscal),
+            float(kl_weight), int(parts), _lib.ptr(gZ), _lib.ptr(ghyp), _lib.ptr(gqmu), _lib.ptr(gqsqrt), _lib.ptr(ws), ws.numel(),
+            _lib.stream()))
+
+    def m_only_static(self, kl_weight=1.0, hyp=None):
+        """The part of the chain rule that depends only on the parameters and on this step's dcgp_layer_prepare (the KL
+        gradient): everything that can be computed BEFORE the layer's dS / dalpha exist.  TrainStep queues it on the layer's
+        side stream during the forward pass.  `hyp`: device tensor [variance, lengthscale] (else the host's values)."""
+        if not self.NATIVE:
+            return self.m_only_static_torch(kl_weight, hyp)
+        self._chain(1, kl_weight, hyp)
+        return True
+
+    def m_only(self, kl_weight=1.0, hyp=None, static=None):
+        """Chain rule through the minibatch-independent operands (csrc/dcgp_chain.cu has the algebra): returns
+        d ELBO / d{Z, variance, lengthscale, q_mu, q_sqrt (lower), patch_weights}.  `kl_weight` = 1/world_size so that summing
+        over ranks counts the KL once.  `hyp` (optional): device tensor [variance, lengthscale] to use instead of the host
+        floats -- keeps the chain free of host values so that it can be captured in a CUDA graph (TrainStep).  `static`: the
+        token returned by m_only_static() for the same parameters (both parts run here when absent)."""
+        if not self.NATIVE:
+            return self.m_only_torch(kl_weight, hyp, static)
+        self._chain(2 if static else 3, kl_weight, hyp)
+        gZ, ghyp, gqmu, gqsqrt = self._chain_out
+        out = {"Z": gZ, "variance": ghyp[0], "lengthscale": ghyp[1], "q_mu": gqmu, "q_sqrt": gqsqrt}
+        if self.layer._kind == _lib.LAYER_SVGP_CONV:
+            out["patch_weights"] = self.gw.clone()
+        return out
+
     def _views(self):
         """Views of this step's float64 factors inside the workspace of the layer's last dcgp_layer_prepare -- Kuu^-1 [M,M],
         Lm [M,M] (lower), Lm^-1 [M,M] (lower), the prior's Lp^-1 [M,M] -- and of the float32 tensor-core products it left in
@@ -160,8 +207,9 @@ class LayerBackward(object):
         return torch.bmm(A3, B3.transpose(1, 2)).sum(0)
 
     @torch.no_grad()
-    def m_only_static(self, kl_weight=1.0, hyp=None):
-        """The part of the chain rule that depends only on the parameters and on this step's dcgp_layer_prepare -- Kuu and its
+    def m_only_static_torch(self, kl_weight=1.0, hyp=None):
+        """(torch restatement of the native chain rule, kept as its cross-check: tests/test_gpu_backward_pieces.py)
+        The part of the chain rule that depends only on the parameters and on this step's dcgp_layer_prepare -- Kuu and its
         distance matrix, the KL gradient, the operand casts -- i.e. everything that can be computed BEFORE the layer's
         dS / dalpha exist.  TrainStep runs it on the layer's side stream during the forward pass, which takes ~40 % of the
         chain off the serial tail of the step."""
@@ -211,8 +259,9 @@ class LayerBackward(object):
                     gls_p=gls_p)
 
     @torch.no_grad()
-    def m_only(self, kl_weight=1.0, hyp=None, static=None):
-        """Chain rule through the minibatch-independent operands, in the order of the forward (conditionals.py:29-58):
+    def m_only_torch(self, kl_weight=1.0, hyp=None, static=None):
+        """(torch restatement of the native chain rule, kept as its cross-check)
+        Chain rule through the minibatch-independent operands, in the order of the forward (conditionals.py:29-58):
              Lm = chol(Kuu), Li = Lm^-1, a = Li k;  C_r = Li L_r (L_r when whitened), S_r = C_r C_r^T, alpha = Li q_mu (q_mu)
            mean_r = alpha_r^T a,  var_r = knn - |a|^2 + a^T S_r a.
         Inputs (dcgp_layer_backward): dS_r = sum_t s_r a a^T, dalpha = sum_t a g_mean^T, and the direct paths gZ, gscal, gw.
@@ -227,7 +276,7 @@ class LayerBackward(object):
         layer = self.layer
         M, R, Mp = self.M, self.R, self.Mp
         white = layer.white
-        st = static if static is not None else self.m_only_static(kl_weight, hyp)
+        st = static if static is not None else self.m_only_static_torch(kl_weight, hyp)
         bt = self.BATCHED_DTYPE
         gS = self.gQB[Mp:(R + 1) * Mp].reshape(R, Mp, Mp)[:, :M, :M]
         galpha = self.gQB[(R + 1) * Mp:(R + 1) * Mp + R, :M].T              # [M, R]

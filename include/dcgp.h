@@ -187,6 +187,22 @@ int dcgp_layer_backward_phases(const dcgp_layer_desc* d, const void* prep, const
                                const double* patch_weights, const float* X, int n_rows, int n_rep, const float* g_mean,
                                const float* g_var, float* gX, double* gQB, double* gZ, double* gscal, double* gw,
                                void* ws, size_t ws_bytes, int phases, void* stream);
+/* The M-only chain rule of one layer: from dS_r, dalpha (rows of gQB as written by dcgp_layer_backward) and the direct-path
+ * gradients gZ_direct / gscal to the gradients of the ELBO w.r.t. the layer's (constrained) parameters -- through
+ * C_r = Lm^-1 L_r, S_r = C_r C_r^T, alpha = Lm^-1 q_mu, the Cholesky factor (Cholesky backward rule) and the RBF kernel --
+ * plus the gradient of -kl_weight * KL (layers.py:137-147 / DS/layers.py:231-256).  What tf.gradients derives for the
+ * minibatch-independent part of conditionals.py:29-58 when experiment.py:105-108 builds the optimiser.
+ *   prep, prepare_ws : the buffers of this step's dcgp_layer_prepare (algo = DCGP_ALGO_TC): factors and tensor-core products
+ *   hyp              : device {variance, lengthscale} to use instead of the descriptor's values (NULL = the descriptor's);
+ *                      lets the call sit in a CUDA graph that is replayed while the host's copy is one step behind
+ *   parts            : 1 = the parameter-only part (KL gradient; may be queued before the backward pass), 2 = the part that
+ *                      needs gQB / gZ_direct / gscal, 3 = both.  `ws` carries state from part 1 to part 2.
+ *   gZ [M,L], ghyp[2] = {d/dvariance, d/dlengthscale}, g_qmu [M,R], g_qsqrt [R,M,M] (lower triangular): float64 outputs. */
+size_t dcgp_chain_rule_workspace_bytes(const dcgp_layer_desc* d);
+int dcgp_layer_chain_rule(const dcgp_layer_desc* d, const void* prep, const void* prepare_ws, const double* Z,
+                          const double* Z_prior, const double* q_mu, const double* q_sqrt, const double* hyp, const double* gQB,
+                          const double* gZ_direct, const double* gscal, double kl_weight, int parts, double* gZ, double* ghyp,
+                          double* g_qmu, double* g_qsqrt, void* ws, size_t ws_bytes, void* stream);
 /* Batched C[b] = A[b] B[b]^T, float32 in / out, on the split-fp16 tcgen05 GEMM (22-bit products, fp32 accumulation): the
  * R-batched M^3 products of the M-only chain rule (what tf.gradients emits as batched MatMul ops).  A [batch or 1, m, k],
  * B [batch or 1, n, k], C [batch, m, n], all row-major contiguous; a batch stride (in elements) of 0 broadcasts the operand;

@@ -154,8 +154,15 @@ def test_layer_parameter_gradients_vs_float64_autograd(cfg_name, li, N, white):
     errs, lb, layer, lay, ref, (X32, g_mean, g_var) = _run_layer(li, N, cfg_name=cfg_name, white=white)
     refp = _params_reference(lay, X32, g_mean, g_var)
     get = lambda g, k: npy(g[k]) if isinstance(g[k], torch.Tensor) else np.asarray(g[k])
-    got = lb.m_only(kl_weight=0.0)
+    got = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in lb.m_only(kl_weight=0.0).items()}
     e1 = {k: _nw(get(got, k), refp[k]) for k in refp}
+    # the native chain rule (dcgp_layer_chain_rule) against its torch restatement, KL gradient included
+    nat = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in lb.m_only(kl_weight=0.5).items()}
+    tor = lb.m_only_torch(kl_weight=0.5)
+    e0 = {k: _nw(get(nat, k), get(tor, k)) for k in refp}
+    print("\n%s layer %d white=%s native vs torch chain rule (with KL), normwise: %s" % (cfg_name, li, white, {k: "%.1e" % v for k, v in e0.items()}))
+    for k, e in e0.items():
+        assert e <= 2e-5, ("native vs torch", k, e)
     print("\n%s layer %d white=%s parameter gradients, normwise: %s" % (cfg_name, li, white, {k: "%.1e" % v for k, v in e1.items()}))
     M, R, Mp = lay["M"], lay["R"], lb.Mp
     lb.gQB.zero_()
@@ -165,7 +172,7 @@ def test_layer_parameter_gradients_vs_float64_autograd(cfg_name, li, N, white):
     lb.gscal[0], lb.gscal[1] = float(ref["variance"]), float(ref["lengthscale"])
     if lay["type"] != "conv":
         lb.gw.copy_(torch.as_tensor(ref["patch_weights"], device=dev()))
-    got2 = lb.m_only(kl_weight=0.0)
+    got2 = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in lb.m_only(kl_weight=0.0).items()}
     e2 = {k: _nw(get(got2, k), refp[k]) for k in refp}
     print("%s layer %d white=%s chain rule with exact pieces, normwise: %s" % (cfg_name, li, white, {k: "%.1e" % v for k, v in e2.items()}))
     for k, e in e2.items():
