@@ -32,13 +32,14 @@ int check_launch(const char* what, int n_launched) {
 // ------------------------------------------------------------------------------------------ GEMM
 // 64x64 output tile, 16-deep k-slices, 4x4 outputs per thread; the next slice's global loads are issued into registers
 // before the current slice is consumed (software double buffering) because these GEMMs are small and latency-bound.
+constexpr int KC = 32;    // k-slice depth staged per iteration
 __device__ __forceinline__ void gemm_f64_fetch(const GemmF64& g, const double* __restrict__ A, const double* __restrict__ B,
-                                               int i0, int j0, int k0, int tid, double (&ra)[4], double (&rb)[4]) {
+                                               int i0, int j0, int k0, int tid, double (&ra)[8], double (&rb)[8]) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int e = 0; e < 8; ++e) {
     const int idx = tid + e * 256;
     int i, kk;
-    if (!g.transA) { i = idx >> 4; kk = idx & 15; } else { kk = idx >> 6; i = idx & 63; }
+    if (!g.transA) { i = idx >> 5; kk = idx & 31; } else { kk = idx >> 6; i = idx & 63; }
     const int gi = i0 + i, gk = k0 + kk;
     double v = 0.0;
     if (gi < g.m && gk < g.k) {
@@ -47,7 +48,7 @@ __device__ __forceinline__ void gemm_f64_fetch(const GemmF64& g, const double* _
     }
     ra[e] = v;
     int j, kb;
-    if (!g.transB) { kb = idx >> 6; j = idx & 63; } else { j = idx >> 4; kb = idx & 15; }
+    if (!g.transB) { kb = idx >> 6; j = idx & 63; } else { j = idx >> 5; kb = idx & 31; }
     const int gj = j0 + j, gkb = k0 + kb;
     double w = 0.0;
     if (gj < g.n && gkb < g.k) {
@@ -66,11 +67,11 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-// 64x64 output tile per CTA, 16-deep k-slices staged through shared memory (register double buffering of the global loads:
+// 64x64 output tile per CTA, 32-deep k-slices staged through shared memory (register double buffering of the global loads:
 // these GEMMs are small and latency-bound), inner product on DMMA: 8 warps as 4 (m) x 2 (n), each 16 x 32 = 2 x 4 m8n8 tiles.
 __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
-  __shared__ double As[16][64 + 2];
-  __shared__ double Bs[16][64 + 2];
+  __shared__ double As[KC][64 + 2];
+  __shared__ double Bs[KC][64 + 2];
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   if (g.lowerC && j0 > i0 + 63) return;   // output tile strictly above the diagonal: not needed
   const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
@@ -87,22 +88,22 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
 
   // k-range that can be non-zero given triangular operands (block-uniform)
   int kbeg = 0, kend = g.k;
-  if (g.lowerA) { if (!g.transA) kend = min(kend, i0 + 64); else kbeg = max(kbeg, i0 & ~15); }
-  if (g.lowerB) { if (!g.transB) kbeg = max(kbeg, j0 & ~15); else kend = min(kend, j0 + 64); }
+  if (g.lowerA) { if (!g.transA) kend = min(kend, i0 + 64); else kbeg = max(kbeg, i0 & ~(KC - 1)); }
+  if (g.lowerB) { if (!g.transB) kbeg = max(kbeg, j0 & ~(KC - 1)); else kend = min(kend, j0 + 64); }
 
-  double ra[4], rb[4];
+  double ra[8], rb[8];
   if (kbeg < kend) gemm_f64_fetch(g, A, B, i0, j0, kbeg, tid, ra, rb);
-  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+  for (int k0 = kbeg; k0 < kend; k0 += KC) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < 8; ++e) {
       const int idx = tid + e * 256;
-      if (!g.transA) As[idx & 15][idx >> 4] = ra[e]; else As[idx >> 6][idx & 63] = ra[e];
-      if (!g.transB) Bs[idx >> 6][idx & 63] = rb[e]; else Bs[idx & 15][idx >> 4] = rb[e];
+      if (!g.transA) As[idx & 31][idx >> 5] = ra[e]; else As[idx >> 6][idx & 63] = ra[e];
+      if (!g.transB) Bs[idx >> 6][idx & 63] = rb[e]; else Bs[idx & 31][idx >> 5] = rb[e];
     }
     __syncthreads();
-    if (k0 + 16 < kend) gemm_f64_fetch(g, A, B, i0, j0, k0 + 16, tid, ra, rb);
+    if (k0 + KC < kend) gemm_f64_fetch(g, A, B, i0, j0, k0 + KC, tid, ra, rb);
 #pragma unroll
-    for (int kk = 0; kk < 16; kk += 4) {
+    for (int kk = 0; kk < KC; kk += 4) {
       double a[2], b[4];
 #pragma unroll
       for (int u = 0; u < 2; ++u) a[u] = As[kk + fc][wm + u * 8 + fr];
