@@ -28,6 +28,7 @@ struct GemmF64 {
   double alpha, beta;
   int batch;
   int lowerC;   // only output tiles that touch the lower triangle are computed (symmetric rank-k updates)
+  int ksplit;   // set by gemm_f64(): > 1 = split-k over blockIdx.z with atomic accumulation into a zeroed C
 };
 int gemm_f64(const GemmF64& g, cudaStream_t st);
 

@@ -74,9 +74,12 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
   __shared__ double Bs[KC][64 + 2];
   const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
   if (g.lowerC && j0 > i0 + 63) return;   // output tile strictly above the diagonal: not needed
-  const double* __restrict__ A = g.A + (long long)blockIdx.z * g.strideA;
-  const double* __restrict__ B = g.B + (long long)blockIdx.z * g.strideB;
-  double* __restrict__ C = g.C + (long long)blockIdx.z * g.strideC;
+  // blockIdx.z = batch index, or (g.ksplit > 1, single matrix) the k-split: partial products are added atomically into a
+  // zeroed C -- these GEMMs are latency-bound chains of 16 k-slices on 64 CTAs; splitting k puts 4x the CTAs to work
+  const int bz = g.ksplit > 1 ? 0 : blockIdx.z;
+  const double* __restrict__ A = g.A + (long long)bz * g.strideA;
+  const double* __restrict__ B = g.B + (long long)bz * g.strideB;
+  double* __restrict__ C = g.C + (long long)bz * g.strideC;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;       // this warp's 16 x 32 sub-tile
   const int fr = lane >> 2, fc = lane & 3;
@@ -90,6 +93,12 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
   int kbeg = 0, kend = g.k;
   if (g.lowerA) { if (!g.transA) kend = min(kend, i0 + 64); else kbeg = max(kbeg, i0 & ~(KC - 1)); }
   if (g.lowerB) { if (!g.transB) kbeg = max(kbeg, j0 & ~(KC - 1)); else kend = min(kend, j0 + 64); }
+  if (g.ksplit > 1) {                      // this CTA's share of the (trimmed) k-range, in whole slices
+    const int slices = (kend - kbeg + KC - 1) / KC, per = (slices + g.ksplit - 1) / g.ksplit;
+    const int s0 = (int)blockIdx.z * per;
+    kbeg = kbeg + s0 * KC;
+    kend = min(kend, kbeg + per * KC);
+  }
 
   double ra[8], rb[8];
   if (kbeg < kend) gemm_f64_fetch(g, A, B, i0, j0, kbeg, tid, ra, rb);
@@ -128,15 +137,21 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmF64 g) {
         if (gj >= g.n) continue;
         double* p = C + (long long)gi * g.ldc + gj;
         double r = g.alpha * acc[u][v][e];
+        if (g.ksplit > 1) { if (kbeg < kend) atomicAdd(p, r); continue; }
         if (g.beta != 0.0) r += g.beta * (*p);
         *p = r;
       }
   }
 }
 
-int gemm_f64(const GemmF64& g, cudaStream_t st) {
-  if (g.m <= 0 || g.n <= 0 || g.batch <= 0) return DCGP_OK;
-  dim3 grid(ceil_div(g.n, 64), ceil_div(g.m, 64), g.batch);
+int gemm_f64(const GemmF64& gin, cudaStream_t st) {
+  if (gin.m <= 0 || gin.n <= 0 || gin.batch <= 0) return DCGP_OK;
+  GemmF64 g = gin;
+  const int tiles = ceil_div(g.n, 64) * ceil_div(g.m, 64);
+  g.ksplit = 1;
+  if (g.batch == 1 && g.beta == 0.0 && !g.lowerC && g.k >= 256 && tiles <= 96) g.ksplit = g.k >= 512 ? 4 : 2;
+  dim3 grid(ceil_div(g.n, 64), ceil_div(g.m, 64), g.ksplit > 1 ? g.ksplit : g.batch);
+  if (g.ksplit > 1) cudaMemset2DAsync(g.C, (size_t)g.ldc * sizeof(double), 0, (size_t)g.n * sizeof(double), (size_t)g.m, st);
   gemm_f64_kernel<<<grid, 256, 0, st>>>(g);
   return check_launch("gemm_f64");
 }
