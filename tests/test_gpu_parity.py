@@ -296,10 +296,10 @@ def test_convlayer_vs_oracle(cfg, algo):
 @pytest.mark.parametrize("algo", ALGOS)
 def test_ill_conditioned_kuu(algo):
     """1024 inducing patches in a 32-dimensional patch space: cond(Kuu) ~ 1e4.  The reference is float64; the T-sized
-    arithmetic here is fp32-class, so the error grows with the cancellation in Lm^-1 k.  The fp32 CUDA-core path still
-    meets the 1e-4 gate; the tensor-core path accumulates 3*M/16 MMAs per output in TMEM with round-toward-zero
-    accumulation, whose bias scales with the same cancellation: documented bound 1e-3 at this conditioning
-    (DESIGN.md, "precision")."""
+    arithmetic here is fp32-class, so the error grows with the cancellation in Lm^-1 k.  The fp32 CUDA-core path meets the
+    1e-4 gate (measured 4.7e-5 / 5e-6).  The tensor-core path accumulates 3*M/16 MMAs per output in TMEM, which rounds
+    toward zero (tools/diag_accum.py: 0.69 ulp low per MMA); that bias is amplified by the same cancellation: measured
+    1.7e-4 (mean) / 3.2e-5 (var), gated at 3e-4 ("Precision")."""
     from oracle import dcgp_oracle as O
     rng = np.random.RandomState(1234)
     lay = _synthetic_conv(rng, 12, 12, 2, 4, 3, 1024, 4, trained=True)
@@ -307,7 +307,7 @@ def test_ill_conditioned_kuu(algo):
     mref, vref = O.convlayer_conditional_ND_fast(X.astype(np.float64), lay)
     mean, var = build_conv(lay, algo).conditional_ND(torch.as_tensor(X, device=dev()))
     from tests.util import parity_err
-    bound = 1e-4 if algo == "simt" else 1e-3
+    bound = 1e-4 if algo == "simt" else 3e-4
     for got, ref, what in ((mean, mref, "mean"), (var, vref, "var")):
         normwise, _ = parity_err(npy(got), ref, 5.0)
         assert normwise <= bound, "%s: normwise %.3e > %.0e" % (what, normwise, bound)
