@@ -531,7 +531,7 @@ def ncu_summary():
 
 def kernel_roofline(model, cfg, B, S, device, flush):
     """Dominant kernel = the tcgen05 conditional GEMM of conv layer 2 (forward): two launches of the same kernel,
-    `tc_kernel<MODE_A,256>` (a = K Lm^-T) + `tc_kernel<MODE_COND,256>` (G_r = a C_r), timed together; the two big
+    `tc_kernel<MODE_AP,128>` (a = K Lm^-T) + `tc_kernel<MODE_COND,256>` (G_r = a C_r), timed together; the two big
     backward GEMMs of the same layer (`dk_gemm_kernel`, `xf_gemm_kernel`) and the Kuf kernel are reported next to it.
     Every kernel is timed live with CUDA events recorded by the library on the launching stream around that launch
     (dcgp_set_kernel_timing), L2 flushed before every repetition, on the layer's ACTUAL input (samples of layer 1).
@@ -612,7 +612,7 @@ def kernel_roofline(model, cfg, B, S, device, flush):
     dk = tensor_entry("dk_gemm_kernel<256,EPI_PLANES> + dk_gemm_kernel<256,EPI_DD> (da GEMM, then dK = da Lm^-1 + fused dd epilogue; "
                       "conv layer 2 backward)", "dk_gemm", ms_dk, 2.0 * T * R * M * M + 1.0 * T * M * M, exe[2], also="dk_gemm_stage2")
     dq = tensor_entry("xf_gemm_kernel<256> (dS_r = a^T diag(s_r) a, conv layer 2 backward)", "dq_gemm", ms_dq, 1.0 * T * R * M * M, exe[3])
-    out = {"bound": "tensor", "kernel": "tc_kernel<MODE_A,256> + tc_kernel<MODE_COND,256> (chained conditional GEMM, conv layer 2 forward)",
+    out = {"bound": "tensor", "kernel": "tc_kernel<MODE_AP,128> + tc_kernel<MODE_COND,256> (chained conditional GEMM, conv layer 2 forward)",
            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "ms": ms, "algorithmic_gflop": alg / 1e9,
            "executed_tensor_gflop": exe[0] / 1e9, "executed_tflops": exe[0] / (ms * 1e-3) / 1e12,
            "executed_frac": exe[0] / (ms * 1e-3) / 1e12 / peak, "peak_source": src,

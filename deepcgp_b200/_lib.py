@@ -43,6 +43,8 @@ SIGNATURES = {
     "dcgp_kernel_tensor_flops": (C.c_double, [_i]),
     "dcgp_set_products": (None, [_i, _i, _i]),
     "dcgp_get_products": (None, [C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "dcgp_set_precise_stage1": (None, [_i]),
+    "dcgp_get_precise_stage1": (_i, []),
     "dcgp_view_geometry": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
     "dcgp_extract_patches": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "dcgp_kuu": (_i, [_vp, _i, _i, _d, _d, _d, _vp, _vp]),

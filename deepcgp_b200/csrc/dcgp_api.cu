@@ -226,6 +226,8 @@ void dcgp_set_reserved_sms(int n) { dcgp::tc_set_reserved_sms(n); }
 double dcgp_kernel_ms(int which) { return dcgp::tc_kernel_ms(which); }
 double dcgp_kernel_tensor_flops(int which) { return dcgp::tc_kernel_flops(which); }
 void dcgp_set_products(int cond, int dk, int dq) { dcgp::tc_set_products(cond, dk, dq); }
+void dcgp_set_precise_stage1(int mode) { dcgp::tc_set_precise_stage1(mode); }
+int dcgp_get_precise_stage1(void) { return dcgp::tc_get_precise_stage1(); }
 void dcgp_get_products(int* cond, int* dk, int* dq) {
   const dcgp::TcProducts& t = dcgp::tc_products();
   if (cond) *cond = t.cond;

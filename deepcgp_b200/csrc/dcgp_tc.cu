@@ -170,6 +170,20 @@ constexpr int MODE_COND = 0;   // conditional GEMM: per-row-block sums of square
 constexpr int MODE_GEMM = 1;   // plain batched C = A * B^T: store fp32 and/or accumulate the sum of squares of C
 constexpr int MODE_A = 2;      // chained form, first stage: a = K Lm^-T (lower-triangular operand: zero k-blocks skipped),
                                // acc[t, 0] = |a_t|^2 and the split-fp16 planes of a for the second stage
+constexpr int MODE_AP = 3;     // MODE_A with the accumulation spread over four TMEM accumulators (BN = 128): the TMEM fp32
+                               // accumulator rounds toward zero at every MMA (tools/diag_accum.py), a bias that the cancellation
+                               // in Lm^-1 k amplifies.  The two low-order products go to an accumulator of their own (they are
+                               // 2^-11 of the sum, so their truncations vanish) and the dominant product to up to three
+                               // accumulators over consecutive k-chunks; the epilogue adds the four in fp32 round-to-nearest.
+__host__ __device__ constexpr bool mode_is_a(int mode) { return mode == MODE_A || mode == MODE_AP; }
+template <int MODE, int BN>
+__host__ __device__ constexpr int tmem_cols() { return MODE == MODE_AP ? 4 * BN : 2 * BN; }
+// MODE_AP: k-blocks of tile jt that are full width (the rest straddle the diagonal), and the number of k-chunks in use
+template <int BN>
+__device__ __forceinline__ void ap_chunks(int jt, int kb1, int& nfull, int& nch) {
+  nfull = min(kb1, (jt * BN) / 64);
+  nch = nfull == 0 ? 1 : min(3, nfull);
+}
 
 struct TcParams {
   int n_items;
@@ -210,7 +224,7 @@ struct TcParams {
 template <int MODE, int BN>
 __device__ __forceinline__ int tiles_in_item(const TcParams& p, int item) {
   if (MODE == MODE_COND) { const int per = p.R + 2 - p.blk_first; return (item % per == per - 1) ? 1 : p.njt; }
-  if (MODE == MODE_A) return p.njt;
+  if (mode_is_a(MODE)) return p.njt;
   return 1;
 }
 template <int MODE, int BN>
@@ -220,7 +234,7 @@ __device__ __forceinline__ void tile_rows(const TcParams& p, int item, int jt, i
     const int tt = item / per, blk = p.blk_first + item - tt * per;
     a_row = tt * kBM;
     b_row = blk * p.Mp + jt * BN;
-  } else if (MODE == MODE_A) {
+  } else if (mode_is_a(MODE)) {
     a_row = item * kBM;
     b_row = jt * BN;
   } else {
@@ -236,7 +250,7 @@ __device__ __forceinline__ void tile_rows(const TcParams& p, int item, int jt, i
 template <int MODE, int BN>
 __device__ __forceinline__ void item_krange(const TcParams& p, int item, int jt, int& kb0, int& kb1) {
   kb0 = 0; kb1 = p.nkb;
-  if (MODE == MODE_A) kb1 = min(p.nkb, ((jt + 1) * BN + kBK - 1) / kBK);          // Lm^-1[j, m] = 0 for m > j
+  if (mode_is_a(MODE)) kb1 = min(p.nkb, ((jt + 1) * BN + kBK - 1) / kBK);          // Lm^-1[j, m] = 0 for m > j
   if (MODE == MODE_COND && p.tri == 2) {
     const int per = p.R + 2 - p.blk_first;
     if (item % per != per - 1) kb0 = (jt * BN) / kBK;                              // C_r^T[j, i] = 0 for i < j
@@ -270,7 +284,7 @@ __device__ __forceinline__ bool mean_item(const TcParams& p, int item) {   // MO
 template <int MODE, int BN>
 __device__ __forceinline__ void kb_cols(const TcParams& p, bool desc, int jt, int kb, int& col_off, int& n) {
   col_off = 0; n = BN;
-  if (MODE == MODE_A) { col_off = max(0, kb * kBK - jt * BN); n = BN - col_off; }
+  if (mode_is_a(MODE)) { col_off = max(0, kb * kBK - jt * BN); n = BN - col_off; }
   if (MODE == MODE_COND && desc) n = min(BN, kb * kBK + kBK - jt * BN);
 }
 constexpr int kMaxStages = 8;
@@ -310,7 +324,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_base_smem, Cfg::kTmemCols);
+  if (warp == 1) tmem_alloc(tmem_base_smem, (tmem_cols<MODE, BN>()));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -370,6 +384,44 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
       uint32_t tile = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int njt = tiles_in_item<MODE, BN>(p, item);
+        if (MODE == MODE_AP) {
+          for (int jt = 0; jt < njt; ++jt, ++tile) {
+            mbar_wait(&tmem_empty[0], (tile & 1) ^ 1);      // all four accumulators belong to one tile: no MMA / epilogue overlap
+            tc_fence_after();
+            int kb0, kb1, nfull, nch;
+            item_krange<MODE, BN>(p, item, jt, kb0, kb1);
+            ap_chunks<BN>(jt, kb1, nfull, nch);
+            uint32_t acc_lo = 0, started = 0;
+            for (int kb = 0; kb < kb1; ++kb) {
+              int col_off, n;
+              kb_cols<MODE, BN>(p, false, jt, kb, col_off, n);
+              const int c = kb < nfull ? (kb * nch) / nfull : nch - 1;   // a chunk always starts with a full-width block
+              const uint32_t idesc = idesc0 | ((uint32_t)(n >> 3) << 17);
+              const uint32_t d_lo = tmem_base + col_off, d_hh = tmem_base + (1 + c) * BN + col_off;
+              mbar_wait(&full_bar[stage], phase);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(smem + stage * stage_bytes);
+              const uint32_t a_lo = a_hi + Cfg::kStageA;
+              const uint32_t b_hi = a_hi + 2 * Cfg::kStageA + col_off * (kBK * 2);
+              const uint32_t b_lo = b_hi + Cfg::kStageB;
+              const uint64_t dah = make_sw128_desc(a_hi), dal = make_sw128_desc(a_lo);
+              const uint64_t dbh = make_sw128_desc(b_hi), dbl = make_sw128_desc(b_lo);
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);
+                umma_f16(d_lo, dal + koff, dbh + koff, idesc, acc_lo);
+                acc_lo = 1;
+                umma_f16(d_lo, dah + koff, dbl + koff, idesc, 1);
+                umma_f16(d_hh, dah + koff, dbh + koff, idesc, (started >> c) & 1u);
+                started |= 1u << c;
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == n_stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tmem_full[0]);
+          }
+          continue;
+        }
         const bool desc = tile_descending<MODE, BN>(p, item);
         const bool mean3 = mean_item<MODE, BN>(p, item) && p.nprod != 3;
         const bool two_a = !mean3 && a_planes == 2, two_b = !mean3 && b_planes == 2;
@@ -468,23 +520,41 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
         }
         if (!is_mean && t < p.T) p.acc[(long long)t * (p.R + 1) + blk] = ssq * sq_scale;
       }
-    } else if (MODE == MODE_A) {
+    } else if (mode_is_a(MODE)) {
       const float inv = p.wscal[1] * p.kscal[1];               // accumulator -> a
       const float sa = p.ascal[0];
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const long long t = (long long)item * kBM + q * 32 + lane;   // < Tpad: padding rows hold zeros (K rows are zero)
         float ssq = 0.f;
         for (int jt = 0; jt < p.njt; ++jt, ++tile) {
-          const uint32_t buf = tile & 1, use = tile >> 1;
+          const uint32_t buf = MODE == MODE_AP ? 0u : (tile & 1), use = MODE == MODE_AP ? tile : (tile >> 1);
           mbar_wait(&tmem_full[buf], use & 1);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_base + buf * BN;
           __half* oh = p.Ah_out + t * p.Mp + jt * BN;
           __half* ol = p.Al_out + t * p.Mp + jt * BN;
+          int nch = 0;
+          if (MODE == MODE_AP) {
+            int nfull;
+            ap_chunks<BN>(jt, min(p.nkb, ((jt + 1) * BN + kBK - 1) / kBK), nfull, nch);
+          }
 #pragma unroll 1
           for (int c = 0; c < BN; c += 32) {
             float v[32];
-            tmem_ld_32x32(taddr + c, v);
+            if (MODE == MODE_AP) {     // (chunk 0 + chunk 1 + chunk 2) + low-order products, fp32 round-to-nearest
+              float u[32];
+              tmem_ld_32x32(taddr + BN + c, v);
+              for (int ch = 1; ch < nch; ++ch) {
+                tmem_ld_32x32(taddr + (1 + ch) * BN + c, u);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += u[i];
+              }
+              tmem_ld_32x32(taddr + c, u);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] += u[i];
+            } else {
+              tmem_ld_32x32(taddr + c, v);
+            }
             __align__(16) __half2 hi[16];
             __align__(16) __half2 lo[16];
 #pragma unroll
@@ -567,7 +637,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, (tmem_cols<MODE, BN>()));
   }
 }
 
@@ -670,6 +740,21 @@ void tc_set_products(int cond, int dk, int dq) {
   if (cond >= 1 && cond <= 4) g_prod.cond = cond;
   if (dk >= 1 && dk <= 4) g_prod.dk = dk;
   if (dq >= 1 && dq <= 4) g_prod.dq = dq;
+}
+
+// Stage 1 of the chained conditional with the accumulation spread over four TMEM accumulators (MODE_AP): 1 (default) =
+// whenever M is padded to a multiple of 128, 0 = never, -1 = from kPreciseAutoM inducing points on.  Measured
+// (tools/diag_accum.py): +2 % on the conditional at M = 512, +1 % at M = 1024; mean error at cond(Kuu) = 1e4, M = 1024:
+// 1.7e-4 -> 3.5e-5.  DCGP_PRECISE_STAGE1 / dcgp_set_precise_stage1().
+static int g_precise = -2;
+void tc_set_precise_stage1(int mode) { g_precise = mode < 0 ? -1 : (mode ? 1 : 0); }
+int tc_get_precise_stage1() {
+  if (g_precise == -2) { const char* e = getenv("DCGP_PRECISE_STAGE1"); g_precise = e ? (atoi(e) < 0 ? -1 : (atoi(e) ? 1 : 0)) : 1; }
+  return g_precise;
+}
+bool tc_precise_stage1(int Mp) {
+  const int mode = tc_get_precise_stage1();
+  return mode > 0 || (mode < 0 && Mp >= kPreciseAutoM);
 }
 
 static int num_sms() {
@@ -796,7 +881,18 @@ static int launch_cond_chained(const TcPrep& prep, const TcCondWork& w, int T, i
   p.wscal = prep.scal; p.kscal = w.kscal; p.acc = acc; p.mean = mean;
   p.Ah_out = (__half*)w.Ah; p.Al_out = (__half*)w.Al; p.ascal = w.ascal;
   p.nprod = 3;                                                 // a = Lm^-1 k cancels: always the full 22-bit product
-  if ((rc = launch_tc<MODE_A, BN>(tmKh, tmKl, tmBh, tmBl, tmB64h, tmB64l, p, st))) return rc;
+  if (tc_precise_stage1(Mp) && Mp % 128 == 0) {                // four accumulators of 128 columns (MODE_AP)
+    CUtensorMap tmB128h = tmBh, tmB128l = tmBl;
+    if (BN != 128) {
+      if ((rc = make_tmap_f16(&tmB128h, prep.Wh, w_rows(Mp, R), Mp, 128))) return rc;
+      if ((rc = make_tmap_f16(&tmB128l, prep.Wl, w_rows(Mp, R), Mp, 128))) return rc;
+    }
+    p.njt = Mp / 128;
+    if ((rc = launch_tc<MODE_AP, 128>(tmKh, tmKl, tmB128h, tmB128l, tmB64h, tmB64l, p, st))) return rc;
+    p.njt = Mp / BN;
+  } else if ((rc = launch_tc<MODE_A, BN>(tmKh, tmKl, tmBh, tmBl, tmB64h, tmB64l, p, st))) {
+    return rc;
+  }
   p.n_items = ceil_div(T, kBM) * (R + 1);
   p.blk_first = 1; p.tri = 2; p.kscal = w.ascal;
   p.nprod = nprod2;                                            // G_r = C_r^T a feeds a sum of squares (no cancellation)

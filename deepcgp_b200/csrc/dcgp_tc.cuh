@@ -104,6 +104,10 @@ struct TcProducts { int cond, dk, dq; };
 constexpr int kDefaultProdCond = 3, kDefaultProdDk = 3, kDefaultProdDq = 3;   // measured: tests/test_gpu_bench_size.py, DESIGN.md 'Precision'
 const TcProducts& tc_products();
 void tc_set_products(int cond, int dk, int dq);   // 0 leaves a value unchanged
+constexpr int kPreciseAutoM = 1024;               // mode < 0: stage 1 of the conditional on four accumulators from this M on
+void tc_set_precise_stage1(int mode);             // 1 always (default), 0 never, < 0 from kPreciseAutoM on
+int tc_get_precise_stage1();
+bool tc_precise_stage1(int Mp);
 
 // Workspace of the backward pass of one layer (see dcgp_tc_bwd.inc)
 struct TcBwdWork {

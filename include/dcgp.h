@@ -83,6 +83,15 @@ double dcgp_kernel_tensor_flops(int which);
 void dcgp_set_products(int cond, int dk, int dq);
 void dcgp_get_products(int* cond_host, int* dk_host, int* dq_host);
 
+/* Accumulation of the first stage a = Lm^-1 k (conditionals.py:29-32) on the tensor-core path.  The TMEM fp32 accumulator
+ * rounds toward zero at every MMA; with 3 M / 16 MMAs per output that bias, amplified by the cancellation in Lm^-1 k, reaches
+ * the 1e-4 gate for ill-conditioned Kuu at M >= 1024.  mode 1 (default): the low-order split products and three k-chunks of the
+ * dominant product accumulate separately (four 128-column TMEM accumulators) and are added in fp32 round-to-nearest -- 5x less
+ * bias for 1-2 % of the conditional's time; used whenever M is padded to a multiple of 128.  mode 0: one accumulator.
+ * mode < 0: mode 1 from 1024 inducing points on.  env DCGP_PRECISE_STAGE1; dcgp_get_precise_stage1 returns -1, 0 or 1. */
+void dcgp_set_precise_stage1(int mode);
+int dcgp_get_precise_stage1(void);
+
 /* views.py:56-68 FullView._patch_count/_patch_length/_out_image_size */
 int dcgp_view_geometry(int H, int W, int C, int f, int s, int* OH_host, int* OW_host, int* P_host, int* L_host);
 

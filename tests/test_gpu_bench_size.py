@@ -5,7 +5,8 @@ DS/dgp.py:92-98 driven from conv_gp/experiment.py:97-108).
 
 Gradient gate: per parameter tensor, max|g - ref| <= 1e-3 * max|ref| (+ a floor for gradients that
 vanish analytically) at M = 512; 2e-3 at M = 1024, where cond(Kuu) -- which every fp32-class quantity of the path is exposed
-to through a = Lm^-1 k -- is an order of magnitude larger (measured: <= 5e-5 at cfg3, <= 1.2e-3 at cfg4)."""
+to through a = Lm^-1 k -- is an order of magnitude larger (measured: <= 5e-5 at cfg3, <= 7.1e-4 at cfg4; 1.2e-3 at cfg4 with a single stage-1 accumulator,
+dcgp_set_precise_stage1(0))."""
 import numpy as np
 import pytest
 import torch
@@ -81,7 +82,7 @@ def test_bench_model_forward_elbo_gradients_vs_oracle(cfg_name, N, S):
     print("\n%s gradient normwise errors: %s" % (cfg_name, {k: "%.1e" % v for k, v in rep.items()}))
     assert not bad, bad
     # the instantiations the benchmark times were the ones that ran
-    for frag in ("dk_gemm_kernel<256, 2>", "dk_gemm_kernel<256, 1>", "dk_gemm_kernel<256, 0>", "xf_gemm_kernel<256>", "tc_kernel<2, 256>",
+    for frag in ("dk_gemm_kernel<256, 2>", "dk_gemm_kernel<256, 1>", "dk_gemm_kernel<256, 0>", "xf_gemm_kernel<256>", "tc_kernel<3, 128>",
                  "tc_kernel<0, 256>", "kuf_tc_kernel<256>"):
         assert any(frag in n for n in names), (frag, sorted(n for n in names if "dcgp" in n)[:40])
 

@@ -1,6 +1,7 @@
 """A/B timing of TrainStep settings inside ONE process (run-to-run variance between gpurun boxes is +-0.5 ms):
 alternates the settings in blocks of `--block` steps, `--rounds` times, L2 flushed between steps.
-    python tools/ab_step.py reserve 0 16 32 -1      (DCGP_RESERVE_SMS values; -1 = one CTA per item for the deferred GEMMs)"""
+    python tools/ab_step.py reserve 0 16 32 -1      (DCGP_RESERVE_SMS values; -1 = one CTA per item for the deferred GEMMs)
+    python tools/ab_step.py precise 0 1             (dcgp_set_precise_stage1)"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -24,6 +25,8 @@ for rnd in range(4):
     for v in vals:
         if what == "reserve":
             ts.reserve_sms = v
+        elif what == "precise":          # dcgp_set_precise_stage1: stage 1 of the conditional on four TMEM accumulators
+            D._lib.lib.dcgp_set_precise_stage1(v)
         for _ in range(3):
             step()
         torch.cuda.synchronize()

@@ -25,12 +25,41 @@ def illcond():
     lay = _synthetic_conv(rng, 12, 12, 2, 4, 3, 1024, 4, trained=True)
     X = rng.standard_normal((2, 12 * 12 * 2)).astype(np.float32)
     mref, vref = O.convlayer_conditional_ND_fast(X.astype(np.float64), lay)
-    for algo in ("simt", "tc"):
+    for algo, precise in (("simt", 0), ("tc", 0), ("tc", 1)):
+        _lib.lib.dcgp_set_precise_stage1(precise)
         mean, var = build_conv(lay, algo).conditional_ND(torch.as_tensor(X, device="cuda"))
         em = parity_err(mean.cpu().numpy(), mref, 5.0)[0]
         ev = parity_err(var.cpu().numpy(), vref, 5.0)[0]
         d = mean.cpu().numpy().astype(np.float64) - mref
-        print("illcond %-4s mean %.3e var %.3e | signed mean of (mean - ref) %.3e, rms %.3e" % (algo, em, ev, d.mean(), d.std()))
+        print("illcond %-4s precise=%d mean %.3e var %.3e | signed mean of (mean - ref) %.3e, rms %.3e" % (
+            algo, precise, em, ev, d.mean(), d.std()))
+    _lib.lib.dcgp_set_precise_stage1(-1)
+
+
+def stage1_time():
+    """Conditional (stage 1 + stage 2) of a conv layer at M = 512 / 1024, T = 256 000, with one and four accumulators."""
+    import bench
+    from tests.test_gpu_parity import _synthetic_conv, build_conv
+    for M in (512, 1024):
+        rng = np.random.RandomState(5)
+        lay = _synthetic_conv(rng, 14, 14, 10, 5, 1, M, 10, trained=True)
+        X = torch.as_tensor(rng.standard_normal((2560, 14 * 14 * 10)).astype(np.float32), device="cuda")
+        layer = build_conv(lay, "tc")
+        outs = {}
+        for precise in (0, 1):
+            _lib.lib.dcgp_set_precise_stage1(precise)
+            _lib.lib.dcgp_set_kernel_timing(1)
+            for _ in range(3):
+                mean, var = layer.conditional_ND(X)
+            torch.cuda.synchronize()
+            ms = _lib.lib.dcgp_kernel_ms(0)
+            outs[precise] = (mean.double().cpu(), var.double().cpu())
+            print("M=%d precise=%d: conditional (both stages) %.3f ms" % (M, precise, ms))
+        _lib.lib.dcgp_set_kernel_timing(0)
+        dm = (outs[0][0] - outs[1][0]).abs().max() / outs[1][0].abs().max()
+        dv = (outs[0][1] - outs[1][1]).abs().max() / outs[1][1].abs().max()
+        print("M=%d: precise vs plain mean %.2e var %.2e" % (M, dm, dv))
+    _lib.lib.dcgp_set_precise_stage1(-1)
 
 
 def gemm_nt(A, B):
@@ -66,5 +95,8 @@ def accum():
 
 if __name__ == "__main__":
     torch.zeros(1, device="cuda")
-    accum()
+    if "accum" in sys.argv[1:] or len(sys.argv) == 1:
+        accum()
     illcond()
+    if "time" in sys.argv[1:]:
+        stage1_time()
