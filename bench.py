@@ -618,7 +618,7 @@ def kernel_roofline(model, cfg, B, S, device, flush):
            "executed_frac": exe[0] / (ms * 1e-3) / 1e12 / peak, "peak_source": src,
            "input": "samples of conv layer 1 (the layer's actual input in the benchmark state)"}
     out.update(prof("cond_gemm", "cond_gemm_stage1"))
-    kuf = {"kernel": "kuf_tc_kernel<256> (conv layer 2)", "bound": "hbm", "ms": ms_kuf,
+    kuf = {"kernel": "kuf_tc_kernel<256,PAIR> (conv layer 2)", "bound": "hbm", "ms": ms_kuf,
            "achieved": kuf_bytes / (ms_kuf * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
            "frac": kuf_bytes / (ms_kuf * 1e-3) / 1e9 / hbm, "algorithmic_bytes": kuf_bytes,
            "executed_tensor_gflop": exe[1] / 1e9, "tensor_floor_ms": exe[1] / (peak * 1e12) * 1e3}

@@ -98,6 +98,53 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (base_lane + i), columns [col, col+32).
+// 256-bit global store (sm_100: STG.256), 32-byte aligned
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* ptr, uint32_t* r) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
+// Row-per-lane epilogues (the tcgen05.ld 32x32b layout: lane = tile row) and 16-bit planes [rows, ld]: a 32-column chunk is
+// 64 bytes per row.  Instead of 32 rows x 16 bytes per instruction, lane pairs (rows t, t + 1) access half rows -- each
+// 256-bit instruction covers 64 contiguous bytes of 16 rows, a quarter of the L1 wavefronts -- and swap halves by shuffle.
+// Pointers are to the chunk in the EVEN row of the lane's pair, advanced by 16 columns on the odd lane.
+// store: w[0..15] = the lane's 32 values (2 per word)
+__device__ __forceinline__ void store_chunk_paired(void* even_row, int ld, const uint32_t* w, bool odd) {
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t send = odd ? w[i] : w[8 + i], keep = odd ? w[8 + i] : w[i];
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    a[i] = odd ? recv : keep;        // a: the even row of the pair, b: the odd row
+    b[i] = odd ? keep : recv;
+  }
+  st_global_256(even_row, a);
+  st_global_256(reinterpret_cast<uint16_t*>(even_row) + ld, b);
+}
+// load, in two steps so that several chunks' loads are in flight before the first swap: lo8 / hi8 receive the raw halves,
+// load_chunk_swap turns them into the lane's own columns 0..15 (lo8) and 16..31 (hi8)
+__device__ __forceinline__ void load_chunk_paired(const void* even_row, int ld, uint32_t* lo8, uint32_t* hi8) {
+  ld_global_nc_256(even_row, lo8);
+  ld_global_nc_256(reinterpret_cast<const uint16_t*>(even_row) + ld, hi8);
+}
+__device__ __forceinline__ void load_chunk_swap(uint32_t* lo8, uint32_t* hi8, bool odd) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t a = lo8[i], b = hi8[i];                 // a: my half of the even row, b: my half of the odd row
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? a : b, 1);
+    lo8[i] = odd ? recv : a;
+    hi8[i] = odd ? b : recv;
+  }
+}
+__device__ __forceinline__ void store_planes_paired(__half* oh, __half* ol, int ld, const __half2* hi, const __half2* lo, bool odd) {
+  store_chunk_paired(oh, ld, reinterpret_cast<const uint32_t*>(hi), odd);
+  store_chunk_paired(ol, ld, reinterpret_cast<const uint32_t*>(lo), odd);
+}
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
@@ -531,8 +578,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
           mbar_wait(&tmem_full[buf], use & 1);
           tc_fence_after();
           const uint32_t taddr = tmem_base + lane_base + buf * BN;
-          __half* oh = p.Ah_out + t * p.Mp + jt * BN;
-          __half* ol = p.Al_out + t * p.Mp + jt * BN;
+          const bool odd = lane & 1;                       // row pairs (t - odd, t - odd + 1): see store_planes_paired
+          __half* oh = p.Ah_out + (t - (odd ? 1 : 0)) * p.Mp + jt * BN + (odd ? 16 : 0);
+          __half* ol = p.Al_out + (t - (odd ? 1 : 0)) * p.Mp + jt * BN + (odd ? 16 : 0);
           int nch = 0;
           if (MODE == MODE_AP) {
             int nfull;
@@ -566,11 +614,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CU
               const float2 hf = __half22float2(hi[i]);
               lo[i] = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              reinterpret_cast<uint4*>(oh + c)[i] = reinterpret_cast<uint4*>(hi)[i];
-              reinterpret_cast<uint4*>(ol + c)[i] = reinterpret_cast<uint4*>(lo)[i];
-            }
+            store_planes_paired(oh + c, ol + c, p.Mp, hi, lo, odd);
           }
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
@@ -1511,7 +1555,7 @@ struct KufParams {
   __half* Kh; __half* Kl;   // [Tpad, Mp]
 };
 
-template <int BN>
+template <int BN, bool PAIR>   // PAIR: patch elements 2i, 2i+1 are adjacent, 8-byte aligned floats (even C): float2 gather
 __global__ void __launch_bounds__(kKufThreads, 1)
 kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant__ CUtensorMap tmZ_lo, KufParams p) {
   using Cfg = CondCfg<BN>;
@@ -1583,8 +1627,14 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
           const int base = __shfl_sync(0xffffffffu, my_base, i);
           const float* src = p.X + (base < 0 ? 0 : base);
           const float msk = base < 0 ? 0.f : sc;
-          x0[i] = in0 ? __ldg(src + o0) * msk : 0.f;
-          x1[i] = in1 ? __ldg(src + o1) * msk : 0.f;
+          if (PAIR) {                                 // one coalesced 256-byte warp load per row and k-block
+            const float2 v = in0 ? __ldg(reinterpret_cast<const float2*>(src + o0)) : make_float2(0.f, 0.f);
+            x0[i] = v.x * msk;
+            x1[i] = v.y * msk;
+          } else {
+            x0[i] = in0 ? __ldg(src + o0) * msk : 0.f;
+            x1[i] = in1 ? __ldg(src + o1) * msk : 0.f;
+          }
         }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * Cfg::kStageBytes;
@@ -1673,8 +1723,9 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
       const float xc = xx_s[(tile & 3) * kBM + row];
       const uint32_t taddr = tmem_base + lane_base + buf * BN + chalf * CW;
       const int m0 = jt * BN + chalf * CW;
-      __half* oh = p.Kh + t * p.Mp + m0;
-      __half* ol = p.Kl + t * p.Mp + m0;
+      const bool odd = lane & 1;                     // (row pairs: the even lane's row t and t + 1)
+      __half* oh = p.Kh + (t - (odd ? 1 : 0)) * p.Mp + m0 + (odd ? 16 : 0);
+      __half* ol = p.Kl + (t - (odd ? 1 : 0)) * p.Mp + m0 + (odd ? 16 : 0);
       uint32_t v[2][32];                             // two chunks in flight: the next TMEM read overlaps this chunk's math
       tmem_ld_32x32_nowait(taddr, v[0]);
 #pragma unroll
@@ -1693,11 +1744,7 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
           const float2 hf = __half22float2(hi[i]);
           lo[i] = __floats2half2_rn(k0 - hf.x, k1 - hf.y);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          reinterpret_cast<uint4*>(oh + ch * 32)[i] = reinterpret_cast<uint4*>(hi)[i];
-          reinterpret_cast<uint4*>(ol + ch * 32)[i] = reinterpret_cast<uint4*>(lo)[i];
-        }
+        store_planes_paired(oh + ch * 32, ol + ch * 32, p.Mp, hi, lo, odd);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[buf]);
@@ -1757,18 +1804,21 @@ static int launch_kuf_tc(const TcPrep& prep, const View& v, const float* X, int 
   p.n_items = ceil_div(p.T, kBM) * p.njt;
   p.nkb = ceil_div(v.L, kBK);
   p.inv_ls = inv_ls; p.variance = variance; p.zz = prep.zz; p.kscal = kscal; p.Kh = (__half*)Kh; p.Kl = (__half*)Kl;
+  const bool pair = (v.C % 2 == 0) && (((uintptr_t)X & 7) == 0);
+  if ((((uintptr_t)Kh | (uintptr_t)Kl) & 31) != 0) { set_error("kuf_tc: K planes must be 32-byte aligned"); return DCGP_ERR_ARG; }
   const int smem_bytes = Cfg::kSmemBytes + 8 * kBM * 4 + ceil_div(v.L, kBK) * kBK * 4 + prep.Mp * 4 + 64;
   if (smem_bytes > 227 * 1024) { set_error("kuf_tc: patch length %d too large", v.L); return DCGP_ERR_ARG; }
-  static int attr_bytes = 0;
-  const bool attr = attr_bytes >= smem_bytes;
-  if (!attr) {
-    attr_bytes = smem_bytes;
-    cudaError_t e = cudaFuncSetAttribute(kuf_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  static int attr_bytes[2] = {0, 0};
+  if (attr_bytes[pair] < smem_bytes) {
+    attr_bytes[pair] = smem_bytes;
+    cudaError_t e = pair ? cudaFuncSetAttribute(kuf_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                         : cudaFuncSetAttribute(kuf_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { set_error("kuf_tc smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
   }
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   ScopedTimer timer(1, st);
-  kuf_tc_kernel<BN><<<grid, kKufThreads, smem_bytes, st>>>(tmZh, tmZl, p);
+  if (pair) kuf_tc_kernel<BN, true><<<grid, kKufThreads, smem_bytes, st>>>(tmZh, tmZl, p);
+  else kuf_tc_kernel<BN, false><<<grid, kKufThreads, smem_bytes, st>>>(tmZh, tmZl, p);
   return check_launch("kuf_tc");
 }
 

@@ -83,7 +83,7 @@ def test_bench_model_forward_elbo_gradients_vs_oracle(cfg_name, N, S):
     assert not bad, bad
     # the instantiations the benchmark times were the ones that ran
     for frag in ("dk_gemm_kernel<256, 2>", "dk_gemm_kernel<256, 1>", "dk_gemm_kernel<256, 0>", "xf_gemm_kernel<256>", "tc_kernel<3, 128>",
-                 "tc_kernel<0, 256>", "kuf_tc_kernel<256>"):
+                 "tc_kernel<0, 256>", "kuf_tc_kernel<256, true>", "kuf_tc_kernel<256, false>"):
         assert any(frag in n for n in names), (frag, sorted(n for n in names if "dcgp" in n)[:40])
 
 

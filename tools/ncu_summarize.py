@@ -18,7 +18,7 @@ COLS = ["ID", "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum"
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "sm__cycles_elapsed.max",
         "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum"]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-KEYS = [("cond_gemm_stage1", "tc_kernel<3, 128>"), ("cond_gemm", "tc_kernel<0, 256>"), ("kuf", "kuf_tc_kernel<256>"),
+KEYS = [("cond_gemm_stage1", "tc_kernel<3, 128>"), ("cond_gemm", "tc_kernel<0, 256>"), ("kuf", "kuf_tc_kernel<256, "),
         ("dk_gemm", "dk_gemm_kernel<256, 2>"), ("dk_gemm_stage2", "dk_gemm_kernel<256, 1>"), ("dq_gemm", "xf_gemm_kernel<256>")]
 
 
