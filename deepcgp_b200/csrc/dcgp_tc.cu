@@ -14,6 +14,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "dcgp_tc.cuh"
 
