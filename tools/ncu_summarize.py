@@ -3,7 +3,8 @@ the per-kernel DRAM traffic / tensor-pipe activity that bench.py quotes in `roof
 
     ncu -i gpurun_out/r2_full.ncu-rep --page raw --csv > /tmp/raw.csv
     python tools/ncu_summarize.py /tmp/raw.csv profiles/r2_ncu_full_layer2.csv "<command that was profiled>" """
-import csv, json, os, subprocess, sys
+import csv
+import os, json, os, subprocess, sys
 
 COLS = ["ID", "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "launch__registers_per_thread",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -55,6 +56,7 @@ def main():
         commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
     except Exception:
         commit = ""
+    commit = commit or os.environ.get("DCGP_TREE", "")      # (the GPU box has no .git: the caller passes the commit)
     summ["source"] = "%s (ncu --set full --clock-control none; %s; tree at %s)" % (out_csv, cmd, commit)
     json.dump(summ, open(os.path.join(os.path.dirname(out_csv) or ".", "ncu_summary.json"), "w"), indent=1)
     print(json.dumps(summ, indent=1))
