@@ -277,6 +277,9 @@ def _synthetic_conv(rng, H, W, C, f, s, M, R, white=False, trained=True):
     dict(N=3, H=14, W=14, C=10, f=5, s=1, M=512, R=10, white=False, trained=False),   # cfg3 layer 2, init state
     dict(N=4, H=14, W=14, C=10, f=5, s=1, M=200, R=7, white=True, trained=True),      # ragged M, R; whitened
     dict(N=2, H=16, W=16, C=3, f=5, s=3, M=1024, R=4, white=False, trained=True),     # cfg4-size M
+    dict(N=3, H=12, W=12, C=4, f=3, s=1, M=384, R=5, white=False, trained=True),      # M padded to 128 only (stage 1 on BN=128 maps)
+    dict(N=3, H=12, W=12, C=4, f=3, s=1, M=300, R=5, white=False, trained=True),      # M padded to 320: single-accumulator stage 1
+    dict(N=5, H=9, W=9, C=2, f=3, s=2, M=100, R=3, white=True, trained=True),         # odd row count (T = 80), M padded to 128
 ])
 def test_convlayer_vs_oracle(cfg, algo):
     from oracle import dcgp_oracle as O
