@@ -62,6 +62,7 @@ SIGNATURES = {
     "dcgp_prepare_workspace_layout2": (_i, [_pd, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_i)]),
     "dcgp_layer_prepare": (_i, [_pd, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _vp]),
     "dcgp_layer_prepare_ev": (_i, [_pd, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "dcgp_layer_prepare_hyp": (_i, [_pd, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "dcgp_apply_workspace_bytes": (_sz, [_pd, _i, _i]),
     "dcgp_layer_apply": (_i, [_pd, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dcgp_backward_workspace_bytes": (_sz, [_pd, _i, _i]),

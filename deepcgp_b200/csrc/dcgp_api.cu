@@ -352,6 +352,13 @@ size_t dcgp_prepare_workspace_bytes(const dcgp_layer_desc* d) {
 int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
                           const double* q_sqrt, int algo, void* prep_buf, double* kl, void* ws, size_t ws_bytes, int* info,
                           void* fwd_ready_event, void* stream) {
+  return dcgp_layer_prepare_hyp(d, Z, Z_prior, q_mu, q_sqrt, algo, prep_buf, kl, ws, ws_bytes, info, fwd_ready_event, nullptr,
+                                stream);
+}
+
+int dcgp_layer_prepare_hyp(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
+                           const double* q_sqrt, int algo, void* prep_buf, double* kl, void* ws, size_t ws_bytes, int* info,
+                           void* fwd_ready_event, const double* hyp, void* stream) {
   DCGP_TRY(check_desc(d));
   if (!Z || !q_mu || !q_sqrt || !prep_buf || !kl || !info) { set_error("layer_prepare: null argument"); return DCGP_ERR_ARG; }
   F64Work w = carve_f64(d->M, d->R, ws);
@@ -360,8 +367,8 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
   cudaStream_t st = (cudaStream_t)stream;
   const int M = d->M, R = d->R, L = p.L;
   cudaMemsetAsync(info, 0, sizeof(int), st);
-  DCGP_TRY(rbf_sym_f64(Z, M, L, d->variance, d->lengthscale, d->jitter, w.Kuu, st));   // layers.py:18-21 / DS/layers.py:184
-  DCGP_TRY(launch_pack_z(Z, (long long)M * L, 1.0 / d->lengthscale, p.zs, st));
+  DCGP_TRY(rbf_sym_f64(Z, M, L, d->variance, d->lengthscale, d->jitter, w.Kuu, st, hyp));   // layers.py:18-21 / DS/layers.py:184
+  DCGP_TRY(launch_pack_z(Z, (long long)M * L, 1.0 / d->lengthscale, p.zs, st, hyp));
   // KL prior.  ConvLayer: Kuu at the *initial* Z with the live kernel hyper-parameters (layers.py:149-150, SURVEY
   // App. C3); SVGP_Layer: the current Ku (DS/layers.py:242-256).
   const bool own_prior = (d->kind == DCGP_LAYER_CONV) && Z_prior && Z_prior != Z && !d->white;
@@ -375,7 +382,7 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
     if (!ax->ok) return DCGP_ERR_CUDA;
     cudaEventRecord(ax->fork, st);
     cudaStreamWaitEvent(ax->aux, ax->fork, 0);
-    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, Kp, ax->aux));
+    DCGP_TRY(rbf_sym_f64(Z_prior, M, L, d->variance, d->lengthscale, d->jitter, Kp, ax->aux, hyp));
     DCGP_TRY(potrf_f64(Kp, M, M, w.invDp, info, ax->aux));
     DCGP_TRY(trtri_f64(Kp, M, M, w.invDp, w.Lpinv, w.trws2, ax->aux));
     cudaEventRecord(ax->join, ax->aux);
@@ -401,14 +408,14 @@ int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const doubl
     if (chained) {
       DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, nullptr, 0, d->white ? 1 : 0, nullptr, w.Mq, q_sqrt, w.beta, w.sc + 1,
                                  nullptr, 1, 1, alpha, st));
-      DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+      DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st, hyp));
       if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
       DCGP_TRY(g_and_beta(w, d->white, q_mu, &gi, st));
     } else {                             // dense single-stack forward (diagnostic): W_r = L_r^T G, beta
       DCGP_TRY(g_and_beta(w, d->white, q_mu, &gi, st));
       DCGP_TRY(tc_build_operands(p.tc, w.Linv, w.Mq, gi.G, gi.ldg, d->white ? 1 : 0, nullptr, w.Mq, q_sqrt, w.beta, w.sc + 1,
                                  nullptr, 1, 0, nullptr, st));
-      DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st));
+      DCGP_TRY(tc_pack_z(p.tc, Z, M, L, 1.0 / d->lengthscale, st, hyp));
       if (fwd_ready_event) cudaEventRecord((cudaEvent_t)fwd_ready_event, st);
     }
     if (d->white) {   // Kuu^-1 is read by the host's chain rule even when G = Lm^-1

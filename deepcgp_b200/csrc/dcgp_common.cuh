@@ -33,7 +33,7 @@ struct GemmF64 {
 int gemm_f64(const GemmF64& g, cudaStream_t st);
 
 int rbf_sym_f64(const double* Z, int M, int L, double variance, double lengthscale, double jitter, double* K,
-                cudaStream_t st);
+                cudaStream_t st, const double* hyp = nullptr);
 // In-place blocked left-looking Cholesky (lower). invD: [ceil(M/NB)] inverses of the diagonal blocks (NB*NB each).
 size_t potrf_ws_bytes(int M);
 int potrf_f64(double* A, int lda, int M, double* invD, int* info, cudaStream_t st);

@@ -158,9 +158,13 @@ int gemm_f64(const GemmF64& gin, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------ Kuu
 // layers.py:18-21 / kernels.py:135-136: variance * exp(-0.5 * |zi - zj|^2 / l^2) + jitter * I
+// hyp (nullable): device {variance, lengthscale} that override the by-value pair (a caller that queues this launch before
+// the host knows the step's hyper-parameters: grad.TrainStep)
 __global__ void __launch_bounds__(256) rbf_sym_f64_kernel(const double* __restrict__ Z, int M, int L, double variance,
-                                                          double inv_ls, double jitter, double* __restrict__ K) {
+                                                          double inv_ls, double jitter, double* __restrict__ K,
+                                                          const double* __restrict__ hyp) {
   __shared__ double Zi[16][17], Zj[16][17];
+  if (hyp) { variance = hyp[0]; inv_ls = 1.0 / hyp[1]; }
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int i = blockIdx.y * 16 + ty, j = blockIdx.x * 16 + tx;
   double d = 0.0;
@@ -180,9 +184,9 @@ __global__ void __launch_bounds__(256) rbf_sym_f64_kernel(const double* __restri
 }
 
 int rbf_sym_f64(const double* Z, int M, int L, double variance, double lengthscale, double jitter, double* K,
-                cudaStream_t st) {
+                cudaStream_t st, const double* hyp) {
   dim3 grid(ceil_div(M, 16), ceil_div(M, 16));
-  rbf_sym_f64_kernel<<<grid, 256, 0, st>>>(Z, M, L, variance, 1.0 / lengthscale, jitter, K);
+  rbf_sym_f64_kernel<<<grid, 256, 0, st>>>(Z, M, L, variance, 1.0 / lengthscale, jitter, K, hyp);
   return check_launch("rbf_sym_f64");
 }
 

@@ -48,7 +48,7 @@ int launch_kdiag(const float* X, const View& v, int n_rows, const double* w, flo
 int launch_varexp(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon, double* varexp,
                   double* sum, cudaStream_t st);
 int launch_elbo(const double* sum_varexp, int S, double scale, const double* kls, int n_layers, double* elbo, cudaStream_t st);
-int launch_pack_z(const double* Z, long long n, double inv_ls, float* zs, cudaStream_t st);
+int launch_pack_z(const double* Z, long long n, double inv_ls, float* zs, cudaStream_t st, const double* hyp = nullptr);
 int launch_pack_w(const double* Linv, int ldl, const double* Wr, int M, int Mp, int R, float* W, cudaStream_t st);
 int launch_pack_wmean(const double* beta, int M, int Mp, int R, int RP, float* Wm, cudaStream_t st);
 int launch_multiclass_predict(const float* Fmu, const float* Fvar, const int32_t* Y, int S, int N, int K, double epsilon,

@@ -714,12 +714,14 @@ int launch_elbo(const double* sum_varexp, int S, double scale, const double* kls
 }
 
 // ------------------------------------------------------------------------------------------ packing (f64 -> f32 operands)
-__global__ void pack_z_kernel(const double* __restrict__ Z, long long n, double inv_ls, float* __restrict__ zs) {
+__global__ void pack_z_kernel(const double* __restrict__ Z, long long n, double inv_ls, float* __restrict__ zs,
+                              const double* __restrict__ hyp) {
+  if (hyp) inv_ls = 1.0 / hyp[1];
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
     zs[e] = (float)(Z[e] * inv_ls);
 }
-int launch_pack_z(const double* Z, long long n, double inv_ls, float* zs, cudaStream_t st) {
-  pack_z_kernel<<<148, 256, 0, st>>>(Z, n, inv_ls, zs);
+int launch_pack_z(const double* Z, long long n, double inv_ls, float* zs, cudaStream_t st, const double* hyp) {
+  pack_z_kernel<<<148, 256, 0, st>>>(Z, n, inv_ls, zs, hyp);
   return check_launch("pack_z");
 }
 

@@ -1765,7 +1765,9 @@ kuf_tc_kernel(const __grid_constant__ CUtensorMap tmZ_hi, const __grid_constant_
 
 // Z / lengthscale (x kXScale) as split-fp16 planes [Mp, Lp] (Lp = ceil(L/64)*64, zero padded) and |zs_m|^2 in fp32.
 __global__ void pack_z_f16_kernel(const double* __restrict__ Z, int M, int Mp, int L, int Lp, double inv_ls,
-                                  __half* __restrict__ Zh, __half* __restrict__ Zl, float* __restrict__ zz) {
+                                  __half* __restrict__ Zh, __half* __restrict__ Zl, float* __restrict__ zz,
+                                  const double* __restrict__ hyp) {
+  if (hyp) inv_ls = 1.0 / hyp[1];
   const int m = blockIdx.x;
   double acc = 0.0;
   for (int l = threadIdx.x; l < Lp; l += blockDim.x) {
@@ -1786,12 +1788,13 @@ __global__ void pack_z_f16_kernel(const double* __restrict__ Z, int M, int Mp, i
 }
 
 __global__ void pack_zt_bf16_kernel(const double* __restrict__ Z, int M, int Mp, int L, int Lp, double inv_ls,
-                                    __nv_bfloat16* __restrict__ ZTh, __nv_bfloat16* __restrict__ ZTl);   // dcgp_tc_bwd.inc
+                                    __nv_bfloat16* __restrict__ ZTh, __nv_bfloat16* __restrict__ ZTl,
+                                    const double* __restrict__ hyp);   // dcgp_tc_bwd.inc
 
-int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st) {
-  pack_z_f16_kernel<<<t.Mp, 128, 0, st>>>(Z, M, t.Mp, L, t.Lp, inv_ls, (__half*)t.Zh, (__half*)t.Zl, t.zz);
+int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st, const double* hyp) {
+  pack_z_f16_kernel<<<t.Mp, 128, 0, st>>>(Z, M, t.Mp, L, t.Lp, inv_ls, (__half*)t.Zh, (__half*)t.Zl, t.zz, hyp);
   pack_zt_bf16_kernel<<<grid_for((long long)t.LpT * t.Mp, 2048), 256, 0, st>>>(Z, M, t.Mp, L, t.LpT, inv_ls, (__nv_bfloat16*)t.ZTh,
-                                                                               (__nv_bfloat16*)t.ZTl);
+                                                                               (__nv_bfloat16*)t.ZTl, hyp);
   set_pair_kernel<<<1, 1, 0, st>>>(kXScale, t.scal + 12);
   return check_launch("pack_z_f16", 3);
 }

@@ -38,7 +38,7 @@ int tc_build_operands(const TcPrep& t, const double* Linv, int ldl, const double
                       const double* Kinv, int parts, int chained, const double* alpha, cudaStream_t st);
 // parts: 1 = forward operands, 2 = KL trace + backward operands.  chained: the W blocks 1..R hold C_r^T (C_r = Lm^-1 L_r, or
 // L_r when whitened) and the mean rows alpha^T (alpha = Lm^-1 q_mu, or q_mu) for tc_cond_chained, instead of W_r / beta^T.
-int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st);
+int tc_pack_z(const TcPrep& t, const double* Z, int M, int L, double inv_ls, cudaStream_t st, const double* hyp = nullptr);
 
 struct TcCondWork {
   TcPrep prep;    // only carved by tc_carve_cond (the conditional() API mirror owns its operands)

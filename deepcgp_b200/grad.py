@@ -536,6 +536,8 @@ class Adam(object):
         host.copy_(vals, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.flat.device))
+        self._dev_hyp = getattr(self, "_dev_hyp", {})
+        self._dev_hyp[li] = vals                     # the same pair on the device (layers.prepare(hyp=...))
         return host, ev
 
     def bind(self):
@@ -631,6 +633,7 @@ class TrainStep(object):
         self.opt.bind()
         self.use_graphs = use_graphs
         self.early_static = os.environ.get("DCGP_EARLY_STATIC", "1") != "0"   # diagnostic switch
+        self.early_prepare = os.environ.get("DCGP_EARLY_PREPARE", "1") != "0"  # diagnostic switch (see _chain)
         # SMs the deferred (parameter-only) GEMMs leave to the chains running underneath them (dcgp_set_reserved_sms)
         self.reserve_sms = int(os.environ.get("DCGP_RESERVE_SMS", "0"))
         self._graphs = {"static": {}, "dynamic": {}}
@@ -699,15 +702,22 @@ class TrainStep(object):
                 model._finish_elbo()
                 self._elbo_ready = torch.cuda.Event()
                 self._elbo_ready.record(side)
+            if self.early_prepare:
+                # the next step's prepare right behind the update, hyper-parameters from the device: it no longer waits for
+                # the host to notice the update, read the pair back and launch ~30 kernels one by one
+                layer.prepare(hyp=opt._dev_hyp[i])
+                layer._ready = torch.cuda.Event()
+                layer._ready.record(side)
 
         def finish():
             ev.synchronize()
             v, l = host.tolist()
             layer._base_kernel.variance, layer._base_kernel.lengthscales = v, l
-            with torch.cuda.stream(side):
-                layer.prepare()
-                layer._ready = torch.cuda.Event()
-                layer._ready.record(side)
+            if not self.early_prepare:
+                with torch.cuda.stream(side):
+                    layer.prepare()
+                    layer._ready = torch.cuda.Event()
+                    layer._ready.record(side)
             layer._fresh = True          # consumed (and cleared) by the next forward pass
 
         layer._pending = finish

@@ -214,8 +214,10 @@ class _PatchGPLayer(Layer):
     def _Z_prior(self):
         return None
 
-    def prepare(self, check=False):
-        """Minibatch-independent work of the step (Kuu, Cholesky, L^-1, stacked operand W, KL)."""
+    def prepare(self, check=False, hyp=None):
+        """Minibatch-independent work of the step (Kuu, Cholesky, L^-1, stacked operand W, KL).
+        hyp: device tensor [variance, lengthscale] (float64) that overrides the host's copy of the kernel hyper-parameters --
+        grad.TrainStep queues the next step's prepare behind the optimiser update before it has read them back."""
         d = self._desc()
         dev = self.device
         # Two prepares of one layer share the Kuu / factor / operand buffers: whatever streams they are queued on, the
@@ -233,10 +235,13 @@ class _PatchGPLayer(Layer):
         if self._ev_fwd is None:
             self._ev_fwd = torch.cuda.Event()
             self._ev_fwd.record()               # forces the underlying cudaEvent_t into existence
-        _lib.check(_lib.lib.dcgp_layer_prepare_ev(d, _lib.ptr(Z), _lib.ptr(Zp), _lib.ptr(self._keep[2]),
-                                                  _lib.ptr(self._keep[3]), self._algo(), _lib.ptr(self._prep),
-                                                  _lib.ptr(self._kl), _lib.ptr(ws), ws.numel(), _lib.ptr(self._info),
-                                                  self._ev_fwd.cuda_event, _lib.stream()))
+        if hyp is not None:
+            assert hyp.dtype == torch.float64 and hyp.numel() == 2 and hyp.is_cuda
+            self._keep = self._keep + (hyp,)
+        _lib.check(_lib.lib.dcgp_layer_prepare_hyp(d, _lib.ptr(Z), _lib.ptr(Zp), _lib.ptr(self._keep[2]),
+                                                   _lib.ptr(self._keep[3]), self._algo(), _lib.ptr(self._prep),
+                                                   _lib.ptr(self._kl), _lib.ptr(ws), ws.numel(), _lib.ptr(self._info),
+                                                   self._ev_fwd.cuda_event, _lib.ptr(hyp), _lib.stream()))
         self._ready_fwd = self._ev_fwd          # recorded inside the call, once the forward operands were queued
         self._prep_done = torch.cuda.Event()
         self._prep_done.record(cur)

@@ -156,6 +156,12 @@ int dcgp_layer_prepare(const dcgp_layer_desc* d, const double* Z, const double* 
 int dcgp_layer_prepare_ev(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
                           const double* q_sqrt, int algo, void* prep, double* kl, void* ws, size_t ws_bytes, int* info,
                           void* fwd_ready_event, void* stream);
+/* Same, with the kernel hyper-parameters read from device memory: hyp = {variance, lengthscale} (float64, may be NULL = use
+ * the values in `d`).  For a host that queues the next step's prepare right behind the optimiser update
+ * (experiment.py:97-108 runs them back to back inside one session.run) before it has read the updated values back. */
+int dcgp_layer_prepare_hyp(const dcgp_layer_desc* d, const double* Z, const double* Z_prior, const double* q_mu,
+                           const double* q_sqrt, int algo, void* prep, double* kl, void* ws, size_t ws_bytes, int* info,
+                           void* fwd_ready_event, const double* hyp, void* stream);
 
 /* The minibatch-sized work of one layer: layers.py:96-135 ConvLayer.conditional_ND or
  * DS/layers.py:191-229 SVGP_Layer.conditional_ND (with kernels.py:106-133 Kzx/Kdiag), followed by the

@@ -25,6 +25,8 @@ for rnd in range(4):
     for v in vals:
         if what == "reserve":
             ts.reserve_sms = v
+        elif what == "prepare":          # TrainStep.early_prepare: next-step prepare queued behind the Adam slice (device-side hyp)
+            ts.finish(); ts.early_prepare = bool(v)
         elif what == "precise":          # dcgp_set_precise_stage1: stage 1 of the conditional on four TMEM accumulators
             D._lib.lib.dcgp_set_precise_stage1(v)
         for _ in range(3):
