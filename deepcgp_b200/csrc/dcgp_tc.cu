@@ -1077,12 +1077,33 @@ struct MaxJobs { MaxJob j[4]; };
 __global__ void __launch_bounds__(256) maxabs_jobs_kernel(MaxJobs J) {
   const MaxJob job = J.j[blockIdx.y];
   float m = 0.f;
-  const long long n = job.rows * job.cols;
-  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += 256LL * gridDim.x) {
-    const long long r = e / job.cols;
-    const int c = (int)(e % job.cols);
-    if (job.lower_period > 0 && c > (int)(r % job.lower_period)) continue;
-    m = fmaxf(m, job.f64 ? (float)fabs(((const double*)job.p)[r * job.ld + c]) : fabsf(((const float*)job.p)[r * job.ld + c]));
+  if (job.cols == 1) {                            // flat array: no index arithmetic, 16-byte loads where aligned
+    const long long n = job.rows;
+    if (job.f64) {
+      const double* p = (const double*)job.p;
+      for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n; e += 256LL * gridDim.x) m = fmaxf(m, (float)fabs(p[e]));
+    } else {
+      const float* p = (const float*)job.p;
+      const long long n4 = (((uintptr_t)p & 15) == 0) ? n / 4 : 0;
+      for (long long e = blockIdx.x * 256LL + threadIdx.x; e < n4; e += 256LL * gridDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + e);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+      for (long long e = 4 * n4 + blockIdx.x * 256LL + threadIdx.x; e < n; e += 256LL * gridDim.x) m = fmaxf(m, fabsf(p[e]));
+    }
+  } else {                                        // one warp per row: one division per row instead of three per element
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * 8;
+    for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < job.rows; r += nwarps) {
+      const int cend = job.lower_period > 0 ? min(job.cols, (int)(r % job.lower_period) + 1) : job.cols;
+      if (job.f64) {
+        const double* row = (const double*)job.p + r * job.ld;
+        for (int c = lane; c < cend; c += 32) m = fmaxf(m, (float)fabs(row[c]));
+      } else {
+        const float* row = (const float*)job.p + r * job.ld;
+        for (int c = lane; c < cend; c += 32) m = fmaxf(m, fabsf(row[c]));
+      }
+    }
   }
   m = block_max_256(m);
   if (threadIdx.x == 0) atomic_max_nonneg(job.out, m);
@@ -1107,7 +1128,7 @@ static int maxabs_jobs(const MaxJob* jobs, int n, cudaStream_t st) {
   long long most = 0;
   for (int i = 0; i < n; ++i) { J.j[i] = jobs[i]; const long long e = jobs[i].rows * jobs[i].cols; most = e > most ? e : most; }
   for (int i = n; i < 4; ++i) J.j[i] = jobs[0];
-  maxabs_jobs_kernel<<<dim3(grid_for(most, 4096), n), 256, 0, st>>>(J);
+  maxabs_jobs_kernel<<<dim3(grid_for(most, 2048), n), 256, 0, st>>>(J);
   return check_launch("maxabs_jobs");
 }
 static int maxabs_f64(const double* a, long long rows, int cols, int ld, int lower_period, float* mx, cudaStream_t st) {
@@ -1151,21 +1172,35 @@ static int pack_planes_f64(const double* src, int ld, long long bstride, int row
 }
 
 // fp32 -> split-fp16 planes: dst[b*rows_pad + i, j] = s * src[b*bstride + i*ld + j], zero padding elsewhere
+// One warp per destination row (cols_pad is a multiple of 64): eight columns per lane and step, 16-byte plane stores; the
+// (batch, row) split costs one division per row.
 __global__ void __launch_bounds__(256) pack_planes_f32_kernel(const float* __restrict__ src, int ld, long long bstride, int rows,
                                                               int cols, int batch, int rows_pad, int cols_pad,
                                                               const float* __restrict__ mx, float* __restrict__ scal2,
                                                               __half* __restrict__ Ph, __half* __restrict__ Pl) {
   const float s = pack_scale(mx, scal2);
-  const long long total = (long long)batch * rows_pad * cols_pad;
-  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
-    const int j = (int)(e % cols_pad);
-    const long long q = e / cols_pad;
+  const int lane = threadIdx.x & 31;
+  const long long nrows = (long long)batch * rows_pad, nwarps = (long long)gridDim.x * 8;
+  const bool vec = (((uintptr_t)src & 15) == 0) && (ld % 4 == 0) && (bstride % 4 == 0);
+  for (long long q = blockIdx.x * 8LL + (threadIdx.x >> 5); q < nrows; q += nwarps) {
     const int i = (int)(q % rows_pad), b = (int)(q / rows_pad);
-    const float v = (i < rows && j < cols) ? s * src[b * bstride + (long long)i * ld + j] : 0.f;
-    __half hi, lo;
-    split_f16(v, hi, lo);
-    Ph[e] = hi;
-    Pl[e] = lo;
+    const float* row = src + b * bstride + (long long)i * ld;
+    for (int j0 = 8 * lane; j0 < cols_pad; j0 += 256) {
+      float v[8];
+      if (i < rows && vec && j0 + 8 <= cols) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(row + j0)), c = __ldg(reinterpret_cast<const float4*>(row + j0 + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (i < rows && j0 + u < cols) ? row[j0 + u] : 0.f;
+      }
+      __align__(16) __half hi[8];
+      __align__(16) __half lo[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) split_f16(s * v[u], hi[u], lo[u]);
+      *reinterpret_cast<uint4*>(Ph + q * cols_pad + j0) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(Pl + q * cols_pad + j0) = *reinterpret_cast<const uint4*>(lo);
+    }
   }
 }
 

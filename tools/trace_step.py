@@ -6,7 +6,7 @@ import bench, deepcgp_b200 as D
 from torch.profiler import profile, ProfilerActivity
 tag = sys.argv[1] if len(sys.argv) > 1 else "step"
 seq = len(sys.argv) > 2 and sys.argv[2] == "seq"
-cfg = bench.CONFIGS["cfg3"]; dev = torch.device("cuda:0")
+cfg = bench.CONFIGS[os.environ.get("DCGP_TRACE_CFG", "cfg3")]; dev = torch.device("cuda:0")
 layers = bench.synth_params(cfg); model = bench.build_model(layers, cfg["S"], dev)
 S, B = cfg["S"], cfg["batch"]
 X = torch.randn((B, 3072), device=dev); Y = torch.randint(0, 10, (B,), device=dev, dtype=torch.int32)
