@@ -63,13 +63,21 @@ size_t chain_rule_workspace_bytes(int M, int R, int L) { return carve_chain(M, R
 
 // ------------------------------------------------------------------------------------------ small kernels
 #define GRID_STRIDE(e, total) for (long long e = blockIdx.x * 256LL + threadIdx.x; e < (total); e += 256LL * gridDim.x)
+// index splits in 32-bit arithmetic (every element count here is below 2^31: chain_rule checks R * Mp * Mp): a 64-bit
+// division by a run-time divisor costs ~80 instructions, more than the rest of these element-wise kernels
+__device__ __forceinline__ int div32(long long e, int d, int& rem) {
+  const unsigned u = (unsigned)e, q = u / (unsigned)d;
+  rem = (int)(u - q * (unsigned)d);
+  return (int)q;
+}
 static int blocks_for(long long n) { long long b = (n + 255) / 256; return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b)); }
 
 // dst[i, j] = (float) src[i, j] (or its transpose), [M, M] inside [Mp, Mp] with zero padding; `lower`: keep i >= j of the source
 __global__ void __launch_bounds__(256) to_f32_kernel(const double* __restrict__ src, int ld, int M, int Mp, int transpose, int lower,
                                                      float* __restrict__ dst) {
   GRID_STRIDE(e, (long long)Mp * Mp) {
-    const int j = (int)(e % Mp), i = (int)(e / Mp);
+    int j;
+    const int i = div32(e, Mp, j);
     float v = 0.f;
     if (i < M && j < M) {
       const int r = transpose ? j : i, c = transpose ? i : j;
@@ -81,9 +89,8 @@ __global__ void __launch_bounds__(256) to_f32_kernel(const double* __restrict__ 
 // LqT[(r*Mp + j)*Mp + i] = L_r[i, j] (i >= j)
 __global__ void __launch_bounds__(256) lqt_kernel(const double* __restrict__ q_sqrt, int M, int Mp, int R, float* __restrict__ out) {
   GRID_STRIDE(e, (long long)R * Mp * Mp) {
-    const int i = (int)(e % Mp);
-    const long long q = e / Mp;
-    const int j = (int)(q % Mp), r = (int)(q / Mp);
+    int i, j;
+    const int q = div32(e, Mp, i), r = div32(q, Mp, j);
     out[e] = (i < M && j < M && i >= j) ? (float)q_sqrt[((long long)r * M + i) * M + j] : 0.f;
   }
 }
@@ -91,7 +98,8 @@ __global__ void __launch_bounds__(256) lqt_kernel(const double* __restrict__ q_s
 __global__ void __launch_bounds__(256) dkl_kernel(const double* __restrict__ a, const float* __restrict__ CC, const double* __restrict__ Kpinv,
                                                   int ldk, int M, int Mp, int R, double* __restrict__ dKL) {
   GRID_STRIDE(e, (long long)Mp * Mp) {
-    const int j = (int)(e % Mp), i = (int)(e / Mp);
+    int j;
+    const int i = div32(e, Mp, j);
     double v = 0.0;
     if (i < M && j < M) {
       double aa = 0.0, cc = 0.0;
@@ -107,9 +115,9 @@ __global__ void __launch_bounds__(256) dkl_kernel(const double* __restrict__ a, 
 // gS32[r] = (float) dS_r (blocks 1..R of gQB, ld Mp), zero padded
 __global__ void __launch_bounds__(256) gs32_kernel(const double* __restrict__ gQB, int M, int Mp, int R, float* __restrict__ gS32) {
   GRID_STRIDE(e, (long long)R * Mp * Mp) {
-    const int j = (int)(e % Mp);
-    const long long q = e / Mp;
-    const int i = (int)(q % Mp);
+    int i, j;
+    const int q = div32(e, Mp, j);
+    div32(q, Mp, i);
     gS32[e] = (i < M && j < M) ? (float)gQB[(long long)Mp * Mp + e] : 0.f;
   }
 }
@@ -118,7 +126,8 @@ __global__ void __launch_bounds__(256) w_kernel(const double* __restrict__ alpha
                                                 int M, int Mp, int R, int white, double* __restrict__ W) {
   const double* galpha = gQB + (long long)(R + 1) * Mp * Mp;      // row r: dalpha[:, r]
   GRID_STRIDE(e, (long long)Mp * Mp) {
-    const int j = (int)(e % Mp), i = (int)(e / Mp);
+    int j;
+    const int i = div32(e, Mp, j);
     double v = 0.0;
     if (i < M && j < M) {
       double ts = 0.0, tst = 0.0, gs = 0.0, ag = 0.0, ga = 0.0;
@@ -141,9 +150,8 @@ __global__ void __launch_bounds__(256) gqsqrt_kernel(const float* __restrict__ r
                                                      const float* __restrict__ Cb32, const double* __restrict__ q_sqrt, int M, int Mp,
                                                      int R, int white, double klw, double* __restrict__ out) {
   GRID_STRIDE(e, (long long)R * M * M) {
-    const int j = (int)(e % M);
-    const long long q = e / M;
-    const int i = (int)(q % M), r = (int)(q / M);
+    int i, j;
+    const int q = div32(e, M, j), r = div32(q, M, i);
     double v = 0.0;
     if (i >= j) {
       const double lij = q_sqrt[e];
@@ -164,14 +172,16 @@ __global__ void __launch_bounds__(256) gqmu_white_kernel(const double* __restric
                                                          int R, double klw, double* __restrict__ out) {
   const double* galpha = gQB + (long long)(R + 1) * Mp * Mp;
   GRID_STRIDE(e, (long long)M * R) {
-    const int r = (int)(e % R), i = (int)(e / R);
+    int r;
+    const int i = div32(e, R, r);
     out[e] = galpha[(long long)r * Mp + i] - klw * q_mu[e];
   }
 }
 // Ps = P + P^T with P = Phi(A2) = tril(A2), diagonal halved
 __global__ void __launch_bounds__(256) psym_kernel(const double* __restrict__ A2, int M, int Mp, double* __restrict__ Ps) {
   GRID_STRIDE(e, (long long)Mp * Mp) {
-    const int j = (int)(e % Mp), i = (int)(e / Mp);
+    int j;
+    const int i = div32(e, Mp, j);
     Ps[e] = (i < M && j < M) ? (i >= j ? A2[e] : A2[(long long)j * Mp + i]) : 0.0;
   }
 }
@@ -242,7 +252,8 @@ __global__ void __launch_bounds__(256) rbf_chain_b_kernel(const double* __restri
     ghyp[1] = sc[3] / ls + sc[1] + gscal[1];
   }
   GRID_STRIDE(e, (long long)M * L) {
-    const int i = (int)(e / L);
+    int l_unused;
+    const int i = div32(e, L, l_unused);
     gZ[e] = -(rs[i] * Z[e] - HZ[e]) / (ls * ls) + gZ_direct[e];
   }
 }
@@ -268,6 +279,7 @@ int chain_rule(const dcgp_layer_desc* d, const ChainInputs& in, const double* Z,
   ChainWork c = carve_chain(M, R, L, ws);
   const int Mp = c.Mp;
   const long long mm = (long long)Mp * Mp;
+  if ((long long)(R + 2) * mm >= (1LL << 31) || (long long)M * L >= (1LL << 31)) { set_error("chain_rule: R * M^2 too large"); return DCGP_ERR_ARG; }
   const double* hyp = hyp_dev;
   if (!hyp) {                       // the descriptor's values (host-current): stage them in the workspace
     set_hyp_kernel<<<1, 1, 0, st>>>(d->variance, d->lengthscale, c.sc + 6);

@@ -1060,6 +1060,13 @@ __global__ void set_scale_kernel(float bound, float* __restrict__ scal2) {
 }
 // scale pair of a plane set from the running maximum of its source (largest entry -> [2^13, 2^14)); the kernel that packs
 // the planes computes it itself from the maximum (no separate launch) and publishes {scale, 1/scale} for the GEMM epilogues
+// index split in 32-bit arithmetic for the element-wise packing kernels (their element counts are below 2^31; a 64-bit
+// division by a run-time divisor costs more than the rest of such a kernel)
+__device__ __forceinline__ int div32(long long e, int d, int& rem) {
+  const unsigned u = (unsigned)e, q = u / (unsigned)d;
+  rem = (int)(u - q * (unsigned)d);
+  return (int)q;
+}
 __device__ __forceinline__ float scale_from_max(float m) {
   int e = 0;
   if (m > 0.f && isfinite(m)) frexpf(m, &e);
@@ -1150,9 +1157,8 @@ __global__ void __launch_bounds__(256) pack_planes_f64_kernel(const double* __re
   const double s = (double)pack_scale(mx, scal2);
   const long long total = (long long)batch * rows_pad * cols_pad;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
-    const int j = (int)(e % cols_pad);
-    const long long q = e / cols_pad;
-    const int i = (int)(q % rows_pad), b = (int)(q / rows_pad);
+    int i, j;
+    const int q = div32(e, cols_pad, j), b = div32(q, rows_pad, i);
     double v = 0.0;
     if (i < rows && j < cols) {
       const int sr = transpose ? j : i, sc = transpose ? i : j;
@@ -1214,12 +1220,13 @@ __global__ void pack_w_f16_kernel(const double* __restrict__ Linv, int ldl, cons
   const double sw = (double)pack_scale(mx, scal), swm = (double)pack_scale(mx ? mx + 1 : nullptr, scal + 2);
   const long long total = rows_total * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(e % Mp);
-    const long long row = e / Mp;
+    int j;
+    const long long row = div32(e, Mp, j);
     double v = 0.0;
     if (j < M) {
       if (row < (long long)(R + 1) * Mp) {
-        const int blk = (int)(row / Mp), i = (int)(row % Mp);
+        int i;
+        const int blk = div32(row, Mp, i);
         if (i < M) {
           if (blk == 0) v = sw * Linv[(long long)i * ldl + j];
           else if (Wr64) v = sw * Wr64[((long long)(blk - 1) * M + i) * M + j];
@@ -1258,11 +1265,12 @@ __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float*
   const long long rows = (long long)R * Mp + 256;
   const long long total = rows * Mp;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(e % Mp);
-    const long long row = e / Mp;
+    int j;
+    const long long row = div32(e, Mp, j);
     double v = 0.0;
     if (row < (long long)R * Mp) {
-      const int r = (int)(row / Mp), i = (int)(row % Mp);
+      int i;
+      const int r = div32(row, Mp, i);
       if (i < M && j < M) v = 2.0 * sc * ((double)Qr[((long long)r * Mp + i) * Mp + j] - (Kinv ? Kinv[(long long)i * M + j] : (i == j ? 1.0 : 0.0)));
     }
     const __half hi = __float2half_rn((float)v);
