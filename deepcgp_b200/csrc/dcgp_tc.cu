@@ -1290,17 +1290,35 @@ __global__ void pack_qp_f16_kernel(const double* __restrict__ Kinv, const float*
 // kblocked: the output planes are k-blocked [Mp/64][Tpad rows][64] (see tma_load_kb) instead of row-major [Tpad, Mp]
 __global__ void split_rows_kernel(const float* __restrict__ Kt, long long T, int Mp, long long Tpad, const float* __restrict__ mx,
                                   float* __restrict__ kscal, __half* __restrict__ Kh, __half* __restrict__ Kl, int kblocked = 0) {
+  // eight consecutive columns per thread (Mp is a multiple of 64): 2 x 16-byte loads, one 16-byte store per plane
   const float s = pack_scale(mx, kscal);
-  const long long total = Tpad * Mp;
+  const int g8 = Mp >> 3;
+  const long long total = Tpad * g8;
+  const bool vec = ((uintptr_t)Kt & 15) == 0;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long t = e / Mp;
-    const float x = (t < T) ? Kt[e] * s : 0.f;
-    __half hi, lo;
-    split_f16(x, hi, lo);
-    const int c = (int)(e - t * Mp);
-    const long long o = kblocked ? ((long long)(c >> 6) * Tpad + t) * 64 + (c & 63) : e;
-    Kh[o] = hi;
-    Kl[o] = lo;
+    const long long t = e / g8;
+    const int c = (int)(e - t * g8) << 3;
+    float v[8];
+    if (t < T) {
+      const float* src = Kt + t * Mp + c;
+      if (vec) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[u];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = 0.f;
+    }
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) split_f16(v[u] * s, hi[u], lo[u]);
+    const long long o = kblocked ? ((long long)(c >> 6) * Tpad + t) * 64 + (c & 63) : t * Mp + c;
+    *reinterpret_cast<uint4*>(Kh + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(Kl + o) = *reinterpret_cast<const uint4*>(lo);
   }
 }
 
