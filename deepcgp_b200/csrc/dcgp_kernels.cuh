@@ -28,6 +28,67 @@ static inline View make_view(int H, int W, int C, int f, int s) {
   return v;
 }
 
+// Squared distances between all pairs of patches of ONE image held in shared memory (kernels.py:106-115, Kdiag and its
+// backward): Dm[p * ldm + q] = |x_p - x_q|^2 for q < p.  4 x 4 patch tiles -- eight loads feed sixteen differences per patch
+// element instead of two loads per difference -- each tile by four adjacent lanes that take a quarter of the patch elements
+// each and add up by shuffle in a fixed order (deterministic).  pb[p]: image offset of patch p, off[l]: image offset of patch
+// element l (both in shared memory); every thread of the CTA must call (blockDim.x a multiple of 32).
+#ifdef __CUDACC__
+static __device__ __forceinline__ void patch_pair_sqdist(const float* __restrict__ img, int P, int L, const int* __restrict__ pb,
+                                                         const int* __restrict__ off, float* __restrict__ Dm, int ldm) {
+  const int nb = (P + 3) >> 2, ntiles = nb * (nb + 1) / 2, per_round = blockDim.x >> 2;
+  const int sub = threadIdx.x & 3;
+  const int l0 = (L * sub) >> 2, l1 = (L * (sub + 1)) >> 2;
+  for (int t0 = 0; t0 < ntiles; t0 += per_round) {
+    const int tile = t0 + (threadIdx.x >> 2);
+    const bool live = tile < ntiles;
+    int bp = 0, bq = 0;
+    if (live) {                                      // unrank (bp >= bq) from tile = bp (bp + 1) / 2 + bq
+      bp = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+      while (bp * (bp + 1) / 2 > tile) --bp;
+      while ((bp + 1) * (bp + 2) / 2 <= tile) ++bp;
+      bq = tile - bp * (bp + 1) / 2;
+    }
+    int pa[4], qb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { pa[u] = pb[min(4 * bp + u, P - 1)]; qb[u] = pb[min(4 * bq + u, P - 1)]; }
+    float d[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d[i] = 0.f;
+    if (live) {
+      for (int l = l0; l < l1; ++l) {
+        const int o = off[l];
+        float xa[4], xb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xa[u] = img[pa[u] + o]; xb[u] = img[qb[u] + o]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float t = xa[u] - xb[w];
+            d[4 * u + w] = fmaf(t, t, d[4 * u + w]);
+          }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      d[i] += __shfl_xor_sync(0xffffffffu, d[i], 1);
+      d[i] += __shfl_xor_sync(0xffffffffu, d[i], 2);
+    }
+    if (live) {
+      const int p = 4 * bp + sub;                    // lane `sub` stores row `sub` of the tile
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int q = 4 * bq + w;
+        // (d[4 * sub + w] with a compile-time index: select instead of a dynamically indexed register array)
+        const float val = sub == 0 ? d[w] : (sub == 1 ? d[4 + w] : (sub == 2 ? d[8 + w] : d[12 + w]));
+        if (p < P && q < p) Dm[p * ldm + q] = val;
+      }
+    }
+  }
+}
+#endif
+
 // ---- dcgp_simt.cu
 int launch_patches(const float* X, const View& v, int N, int layout, float* out, cudaStream_t st);
 int launch_kuf_simt(const float* X, const View& v, int n_rows, const float* zs, int M, float variance, float inv_ls,

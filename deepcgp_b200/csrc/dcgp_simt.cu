@@ -355,8 +355,19 @@ __global__ void __launch_bounds__(256) kdiag_kernel(const float* __restrict__ X,
   __shared__ double red[8];
   const int n = blockIdx.x;
   const float* __restrict__ img = X + (long long)n * v.HWC;
+  const float* Dm = nullptr;                       // use_smem == 2: pair distances from the tiled pass (patch_pair_sqdist)
   if (use_smem) {
     for (int e = threadIdx.x; e < v.HWC; e += 256) img_s[e] = img[e];
+    if (use_smem == 2) {
+      float* dm = img_s + v.HWC;                   // [P][P + 1]
+      int* pb = reinterpret_cast<int*>(dm + v.P * (v.P + 1));
+      int* off = pb + v.P;
+      for (int e = threadIdx.x; e < v.P; e += 256) pb[e] = v.patch_base(e);
+      for (int e = threadIdx.x; e < v.L; e += 256) off[e] = v.elem_off(e);
+      __syncthreads();
+      patch_pair_sqdist(img_s, v.P, v.L, pb, off, dm, v.P + 1);
+      Dm = dm;
+    }
     __syncthreads();
     img = img_s;
   }
@@ -372,6 +383,8 @@ __global__ void __launch_bounds__(256) kdiag_kernel(const float* __restrict__ X,
     float k;
     if (p == q) {
       k = variance;
+    } else if (Dm) {
+      k = 2.f * variance * expf(-0.5f * Dm[p * (v.P + 1) + q] * inv_ls2);
     } else {
       const float* a = img + v.patch_base(p);
       const float* b = img + v.patch_base(q);
@@ -401,8 +414,10 @@ __global__ void __launch_bounds__(256) kdiag_kernel(const float* __restrict__ X,
 }
 int launch_kdiag(const float* X, const View& v, int n_rows, const double* w, float variance, float inv_ls2, float* out,
                  cudaStream_t st) {
-  const size_t bytes = (size_t)v.HWC * sizeof(float);
-  const int use_smem = bytes <= 200 * 1024;
+  size_t bytes = (size_t)v.HWC * sizeof(float);
+  int use_smem = bytes <= 200 * 1024;
+  const size_t tiled = bytes + ((size_t)v.P * (v.P + 1) + v.P + v.L) * sizeof(float);
+  if (tiled <= 96 * 1024) { use_smem = 2; bytes = tiled; }     // image + pair-distance matrix + im2col tables
   if (use_smem && bytes > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kdiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) { set_error("kdiag smem attr: %s", cudaGetErrorString(e)); return DCGP_ERR_CUDA; }
