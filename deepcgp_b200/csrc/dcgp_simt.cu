@@ -278,8 +278,14 @@ __global__ void finalize_kernel(const float* __restrict__ acc, const float* __re
   const long long per = (long long)T * R;
   const long long total = per * n_rep;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long i = e % per;
-    const int t = (int)(i / R), r = (int)(i % R);
+    long long i;
+    int t, r;
+    if (total < (1LL << 32)) {                    // 32-bit index arithmetic (a 64-bit division costs more than the rest of the loop)
+      const unsigned iu = (unsigned)e % (unsigned)per;
+      i = iu; t = (int)(iu / (unsigned)R); r = (int)(iu - (unsigned)t * (unsigned)R);
+    } else {
+      i = e % per; t = (int)(i / R); r = (int)(i % R);
+    }
     const float knn = knn_vec ? knn_vec[t] : knn_const;
     const float m = mean_t[i];
     const float v = knn - acc[(long long)t * (R + 1)] + acc[(long long)t * (R + 1) + 1 + r];
@@ -445,9 +451,17 @@ __global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ z, int S
                                                     long long n0, unsigned long long seed, unsigned long long step, int layer) {
   const long long total = (long long)S * n_local * D;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += 256LL * gridDim.x) {
-    const int d = (int)(e % D);
-    const long long q = e / D;
-    const int n = (int)(q % n_local), s = (int)(q / n_local);
+    int d, n, s;
+    if (total < (1LL << 32)) {
+      const unsigned q = (unsigned)e / (unsigned)D;
+      d = (int)((unsigned)e - q * (unsigned)D);
+      s = (int)(q / (unsigned)n_local);
+      n = (int)(q - (unsigned)s * (unsigned)n_local);
+    } else {
+      d = (int)(e % D);
+      const long long q = e / D;
+      n = (int)(q % n_local); s = (int)(q / n_local);
+    }
     const unsigned long long idx = ((unsigned long long)s * (unsigned long long)n_global + (unsigned long long)(n0 + n)) * D + d;
     uint32_t c[4] = {(uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ ((uint32_t)layer << 16)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
