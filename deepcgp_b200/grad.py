@@ -481,7 +481,7 @@ class Adam(object):
             if name in ("variance", "lengthscale"):
                 u = self._view(self.flat, slot)
                 dst.copy_((g * torch.sigmoid(u)).reshape(1))          # d softplus(u) / du
-            else:
+            elif g.data_ptr() != dst.data_ptr():                      # (TrainStep lets the chain rule write straight into self.grad)
                 dst.copy_(g.reshape(dst.shape))
 
     # ---- per-layer form used by TrainStep (same update rule; the layers' slices of the flat vector are disjoint)
@@ -631,6 +631,12 @@ class TrainStep(object):
         self.eg = ElboGradient(model)
         self.opt = Adam(model, lr=lr, beta1=beta1, beta2=beta2, eps=eps)
         self.opt.bind()
+        # the chain rule's outputs for Z, q_mu, q_sqrt ARE the layers' slices of the optimiser's flat gradient (no copies of
+        # the [R, M, M] q_sqrt gradient per step)
+        for i in range(len(model.layers)):
+            views = {slot[1]: self.opt._view(self.opt.grad, slot) for slot in self.opt.slots if slot[0] == i}
+            self.eg.bwd[i]._chain_out = (views["Z"], torch.zeros(2, dtype=torch.float64, device=model.device), views["q_mu"],
+                                         views["q_sqrt"])
         self.use_graphs = use_graphs
         self.early_static = os.environ.get("DCGP_EARLY_STATIC", "1") != "0"   # diagnostic switch
         self.early_prepare = os.environ.get("DCGP_EARLY_PREPARE", "1") != "0"  # diagnostic switch (see _chain)
