@@ -598,7 +598,7 @@ def kernel_roofline(model, cfg, B, S, device, flush):
         if traffic is not None and e2.get("dram_bytes") is not None:
             traffic += e2["dram_bytes"]
         return {"traffic": traffic, "tensor_pipe_active_pct_ncu": e.get("tensor_pipe_active_pct"),
-                "ncu_source": ncu.get("source")}
+                "ncu_source": e.get("source") or ncu.get("source")}      # (an entry re-captured later names its own file)
 
     def tensor_entry(name, key, t_ms, alg_flops, exe_flops, also=None):
         e = {"kernel": name, "bound": "tensor", "ms": t_ms, "achieved": alg_flops / (t_ms * 1e-3) / 1e12, "peak": peak,
